@@ -72,6 +72,7 @@ typedef struct PobraxParams {
   /* ---- arena walls: axis-aligned boxes in world coordinates (Arena body at z = half height) ---- */
   int32_t num_walls;
   float wall_lo[POBRAX_MAX_WALLS][3], wall_hi[POBRAX_MAX_WALLS][3];
+  float arena_z;            /* z of the frozen Arena body (= wall half height, 0.5) */
   /* ---- task ---- */
   float dying_cost;
   float visible_radius;     /* HeavenHell 2.0, Tag 3.0 */
@@ -99,7 +100,8 @@ typedef struct PobraxState {
   float* first_aux;   /* like aux */
   float* first_obs;   /* like obs  (info['first_obs']) */
   float* ep_return;   /* float[N] running undiscounted return (track_metrics) */
-  double* acc;        /* double[POBRAX_NUM_ACC]: episodes, sum return, sum length, truncations, metric sums */
+  double* acc;        /* double[POBRAX_NUM_ACC]: episodes, sum return, sum length, truncations, hits|apples,
+                         heavens|bombs, hells, dead steps (see csrc/dev_const.h) */
 } PobraxState;
 
 typedef struct PobraxLayout {
@@ -112,9 +114,15 @@ typedef struct PobraxLayout {
 } PobraxLayout;
 
 int pobrax_abi_version(void);
+/* sizeof(PobraxParams), sizeof(PobraxState), sizeof(PobraxLayout): lets an FFI binding verify its struct mirrors. */
+int pobrax_struct_sizes(int32_t* params, int32_t* state, int32_t* layout);
 const char* pobrax_last_error(void);
 
 int pobrax_default_params(int env_kind, PobraxParams* out);
+/* utils.py:60-83 draw_arena(cage_x, cage_y, half_height) and utils.py:87-119 draw_t_maze(t_x, t_y, hallway_width,
+ * half_height), box walls (use_boxes=True): overwrite num_walls / wall_lo / wall_hi of *p. */
+int pobrax_draw_arena(PobraxParams* p, float cage_x, float cage_y, float half_height);
+int pobrax_draw_t_maze(PobraxParams* p, float t_x, float t_y, float hallway_width, float half_height);
 int pobrax_layout(const PobraxParams* p, PobraxLayout* out);
 
 int pobrax_create(const PobraxParams* p, int device, void** handle);
@@ -135,6 +143,10 @@ int pobrax_pack_qp(void* handle, const float* pos, const float* rot, const float
 
 /* jax.random.split(key, n): key = host uint32[2]; out = device uint32[n][2] (rows first..first+count). */
 int pobrax_split_keys(const uint32_t key[2], int n, int first, int count, uint32_t* out, void* stream);
+
+/* Measurement aid (bench.py): one launch of `blocks` x 256 threads x `iters` x 64 dependent-chain FMAs;
+ * *flops = FLOPs of the launch (FMA = 2). out: device float[blocks * 256] scratch. */
+int pobrax_fp32_probe(float* out, int blocks, int iters, void* stream, double* flops);
 
 #ifdef __cplusplus
 }

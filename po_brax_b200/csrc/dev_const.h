@@ -1,47 +1,65 @@
-// Device-side constant block derived on the host from PobraxParams (see ant_system.cpp).
-// Passed to every kernel as a __grid_constant__ parameter (constant bank, LDC-indexable per lane).
+// Device-side constant block derived on the host from PobraxParams (api.cu: build_dev_const).
+// Passed to every kernel by value as a __grid_constant__ parameter (constant bank; uniform loads).
 #pragma once
 #include <stdint.h>
 
 namespace pobrax {
 
 constexpr int kMaxWalls = 8;
-constexpr int kQpPlanes = 32;   // float4 planes per env
-constexpr int kTorsoPlanes = 4; // planes 0..3: torso (13 floats + 3 pad)
-constexpr int kLegPlanes = 7;   // planes 4+7l .. 10+7l: Aux l (13) + lower l (13) + 2 pad
+constexpr int kQpPlanes = 32;   // float4 planes per env in the packed state
 constexpr int kNumAcc = 8;
+constexpr int kMaxObjects = 16; // Gather: n_apples + n_bombs
+constexpr int kMaxBins = 32;    // Gather: 2 * n_bins readings
 
-// aux rows (float[aux_dim][N])
+// ---- packed state: float4 qp[kQpPlanes][N] ------------------------------------------------------
+// planes 0..3   torso:  (px py pz qw) (qx qy qz vx) (vy vz wx wy) (wz - - -)
+// planes 4+7l.. leg l:  A = Aux l (body 1+2l), B = lower leg l (body 2+2l)
+//   +0 (A.px A.py A.pz A.qw) +1 (A.qx A.qy A.qz A.vx) +2 (A.vy A.vz A.wx A.wy) +3 (A.wz B.px B.py B.pz)
+//   +4 (B.qw B.qx B.qy B.qz) +5 (B.vx B.vy B.vz B.wx) +6 (B.wy B.wz - -)
+// ---- aux rows: float aux[aux_dim][N] (frozen bodies that env code moves) ------------------------
 //   Ant        : none
-//   HeavenHell : 0 ground_x, 1 ground_y, 2 target_x (heaven side; hell is the other one)
+//   HeavenHell : 0 ground_x, 1 ground_y, 2 heaven side (0: Target at heaven_hell[0], 1: at heaven_hell[1])
 //   Tag        : 0 ground_x, 1 ground_y, 2 tgt_x, 3 tgt_y, 4 tgt_z
-//   Gather     : 3*k + {0,1,2} = object k xyz (k = 0..15: apples then bombs)
-// metrics rows (float[metrics_dim][N])
+//   Gather     : 3k + {0,1,2} = object k xyz (k = 0..n_apples+n_bombs-1: apples then bombs)
+// ---- metrics rows: float metrics[metrics_dim][N] ------------------------------------------------
 //   Ant        : 0 reward_ctrl_cost, 1 reward_contact_cost, 2 reward_forward, 3 reward_survive
 //   HeavenHell : 0 hits      Tag: 0 hits      Gather: 0 apples, 1 bombs
+// ---- acc: double[kNumAcc] (track_metrics) --------------------------------------------------------
+//   0 finished episodes, 1 sum of episode returns, 2 sum of episode lengths, 3 truncations,
+//   4 hits (HeavenHell: any terminal reward; Tag: tags) / apples caught (Gather),
+//   5 heavens reached (HeavenHell) / bombs caught (Gather), 6 hells reached (HeavenHell),
+//   7 env-steps on which the ant was "dead" (torso z outside [0.2, 1.0])
 
 struct DevConst {
   int32_t n_envs, env_kind, nb, obs_dim, aux_dim, metrics_dim;
-  int32_t episode_length, auto_reset, substeps, track_metrics, n_walls, pad0;
-  float h, dt, gdt /* gravity_z*h */, vel_damp, ang_damp, baumgarte, friction, elasticity;
+  int32_t episode_length, auto_reset, substeps, track_metrics, n_walls, has_rng;
+  float h, dt, gravity_z, vel_damp, ang_damp, baumgarte, friction, elasticity;
   float m_torso, m_leg, inv_m_torso, inv_m_leg, r_torso, r_leg;
   float k_joint, sd_joint, ad_joint, ls_joint, act_strength;
-  float default_angle[8];
-  // per leg l: joint 2l = hip (Torso->Aux), joint 2l+1 = ankle (Aux->lower); offsets have z = 0
-  float hip_op[4][2], hip_oc[4][2], ank_op[4][2], ank_oc[4][2];
-  float ank_ax[4][2];                 // ankle axis (cos phi, sin phi, 0); ankle ref = e_z
-  float foot_e[4][2];                 // lower-leg capsule end (-1) in body frame; the other end is -foot_e
-  float aux_e[4][2];                  // Aux capsule ends are +-aux_e
-  float hip_lo[4], hip_hi[4], ank_lo[4], ank_hi[4];
+  // Leg geometry in factored form (validated at create): every joint offset / capsule end of leg l is a
+  // uniform scalar times the leg's direction u[l] = (ux, uy, 0) in the body frame.
+  float leg_u[4][2];
+  float s_hip_p, s_hip_c, s_ank_p, s_ank_c;  // hip parent/child offset, ankle parent/child offset scales
+  float s_foot, s_aux;                       // lower-leg capsule end (-1) = s_foot*u; Aux ends = +-s_aux*u
+  float seg_aux, seg_foot;                   // capsule half segment lengths (length/2 - r)
+  float ank_ax[4][2];                        // ankle axis (cos phi, sin phi, 0); ankle ref = e_z
+  float hip_lo, hip_hi;                      // hip: axis e_z, ref -e_x, limits uniform over legs
+  float ank_lo[4], ank_hi[4];
+  float hip_default, ank_default[4];         // default_angle(): limit midpoints
+  // walls: axis-aligned boxes in world coordinates + a conservative distance field for exact culling
   float wall_lo[kMaxWalls][3], wall_hi[kMaxWalls][3];
+  const float* sdf;                          // [sdf_ny][sdf_nx] lower bound of xy-distance to the nearest wall
+  float sdf_x0, sdf_y0, sdf_inv_cell;
+  int32_t sdf_nx, sdf_ny;
   // task
   float dying_cost, visible_radius;
-  float hh_xy[2][2], priest_xy[2];
+  float hh_xy[2][2], priest_xy[2], hh_z, priest_z;
   float init_lo[2], init_hi[2];
   float tag_radius, target_step, min_spawn, cage_xy[2];
   int32_t n_apples, n_bombs, n_bins, n_grid;
   float catch_range, sensor_range, half_span, bin_res, spacing, waiting[3];
-  float gather_cage[2];
+  int32_t gather_cx, gather_cy;              // integer cage half extents (grid -cx..cx x -cy..cy)
+  float arena_z;                             // Arena body z (half height)
 };
 
 }  // namespace pobrax

@@ -1,0 +1,757 @@
+// Fused step / reset kernels for the po-brax Ant POMDP envs (sm_100a), plus the small layout kernels.
+//
+// step_kernel<KIND>  = brax.System.step (substeps) + task logic + obs + brax EpisodeWrapper + brax
+//                      AutoResetWrapper in ONE launch:
+//   /root/reference/po_brax/envs/ant_heavenhell.py:106-158, ant_gather.py:125-213, ant_tag.py:107-181,
+//   brax.envs.ant.Ant.step, /root/reference/po_brax/envs/__init__.py:58-68 (wrapper stack).
+// reset_kernel<KIND> = env.reset(rng) under vmap: ant_heavenhell.py:75-103, ant_gather.py:93-123,
+//   ant_tag.py:63-105, brax.envs.ant.Ant.reset (threefry bit-exact), and with only_done=1 the gym-level
+//   autoreset select of /root/reference/po_brax/envs/wrappers.py:245-262.
+//
+// Thread mapping: 4 lanes = 1 env (lane l owns leg l and a replica of the torso); 128 threads = 32 envs.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "../../include/pobrax.h"
+#include "ant_physics.cuh"
+#include "threefry.cuh"
+
+namespace pobrax {
+
+constexpr int kThreads = 128;
+constexpr int kEnvsPerBlock = kThreads / 4;
+
+// ------------------------------------------------------------------------------------------- helpers
+__device__ __forceinline__ float clip1(float x) { return fminf(fmaxf(x, -1.0f), 1.0f); }
+// jp.norm of a 2-vector without FMA contraction (keeps <= radius tests identical to the CPU oracle's)
+__device__ __forceinline__ float norm2_rn(float dx, float dy) {
+  return sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+}
+// jax.random.uniform sample: max(lo, f*(hi-lo)+lo), no contraction
+__device__ __forceinline__ float uniform_rn(uint32_t bits, float lo, float hi) {
+  const float f = bits_to_unit(bits);
+  return fmaxf(lo, __fadd_rn(__fmul_rn(f, __fsub_rn(hi, lo)), lo));
+}
+__device__ __forceinline__ int quad_or(int x) {
+  x |= __shfl_xor_sync(kFull, x, 1);
+  x |= __shfl_xor_sync(kFull, x, 2);
+  return x;
+}
+__device__ __forceinline__ int quad_and(int x) {
+  x &= __shfl_xor_sync(kFull, x, 1);
+  x &= __shfl_xor_sync(kFull, x, 2);
+  return x;
+}
+__device__ __forceinline__ int quad_isum(int x) {
+  x += __shfl_xor_sync(kFull, x, 1);
+  x += __shfl_xor_sync(kFull, x, 2);
+  return x;
+}
+__device__ __forceinline__ float quad_min(float x) {
+  x = fminf(x, __shfl_xor_sync(kFull, x, 1));
+  x = fminf(x, __shfl_xor_sync(kFull, x, 2));
+  return x;
+}
+
+template <int KIND>
+struct ObsCols {
+  static constexpr int P = (KIND == POBRAX_ANT) ? 1 : 3;  // plain Ant observes torso z only
+  static constexpr int rot = P, ja = P + 4, vel = P + 12, ang = P + 15, jv = P + 18, cv = P + 26;
+};
+
+// The part of the observation every env shares: [pos0, rot0, joint angles, vel0, ang0, joint vels,
+// clip(contact.vel), clip(contact.ang)] staged into this env's shared-memory row (pre-zeroed).
+template <int KIND>
+__device__ __forceinline__ void stage_common_obs(float* row, const Rig& r, const LegK& k, const Contact& ct, int leg,
+                                                 const DevConst& C) {
+  using O = ObsCols<KIND>;
+  const Cols cT = rot_cols(r.T), cA = rot_cols(r.A), cB = rot_cols(r.B);
+  float jah, jvh, jaa, jva;
+  joint_angle_vel(r.T, r.A, cT.c2, cT.c0, cA.c0, jah, jvh);
+  const V3 axA = k.axc * cA.c0 + k.axs * cA.c1;
+  joint_angle_vel(r.A, r.B, axA, cA.c2, cB.c2, jaa, jva);
+  row[O::ja + 2 * leg] = jah; row[O::ja + 2 * leg + 1] = jaa;
+  row[O::jv + 2 * leg] = jvh; row[O::jv + 2 * leg + 1] = jva;
+  const int ca = O::cv + 3 * C.nb;
+  if (leg == 0) {
+    if (KIND == POBRAX_ANT) {
+      row[0] = r.T.p.z;
+    } else {
+      row[0] = r.T.p.x; row[1] = r.T.p.y; row[2] = r.T.p.z;
+    }
+    row[O::rot] = r.T.qw; row[O::rot + 1] = r.T.qx; row[O::rot + 2] = r.T.qy; row[O::rot + 3] = r.T.qz;
+    row[O::vel] = r.T.v.x; row[O::vel + 1] = r.T.v.y; row[O::vel + 2] = r.T.v.z;
+    row[O::ang] = r.T.w.x; row[O::ang + 1] = r.T.w.y; row[O::ang + 2] = r.T.w.z;
+    row[O::cv] = clip1(ct.Tv.x); row[O::cv + 1] = clip1(ct.Tv.y); row[O::cv + 2] = clip1(ct.Tv.z);
+    row[ca] = clip1(ct.Tw.x); row[ca + 1] = clip1(ct.Tw.y); row[ca + 2] = clip1(ct.Tw.z);
+  }
+  const int a = 3 * (1 + 2 * leg), b = 3 * (2 + 2 * leg);
+  row[O::cv + a] = clip1(ct.Av.x); row[O::cv + a + 1] = clip1(ct.Av.y); row[O::cv + a + 2] = clip1(ct.Av.z);
+  row[O::cv + b] = clip1(ct.Bv.x); row[O::cv + b + 1] = clip1(ct.Bv.y); row[O::cv + b + 2] = clip1(ct.Bv.z);
+  row[ca + a] = clip1(ct.Aw.x); row[ca + a + 1] = clip1(ct.Aw.y); row[ca + a + 2] = clip1(ct.Aw.z);
+  row[ca + b] = clip1(ct.Bw.x); row[ca + b + 1] = clip1(ct.Bw.y); row[ca + b + 2] = clip1(ct.Bw.z);
+}
+
+// AntGatherEnv._get_readings (ant_gather.py:152-181) for this lane's objects (4 per lane), written in
+// object order 0..n-1 (sequential-scatter semantics: last writer wins, -1 wraps to the last bin).
+__device__ __forceinline__ void gather_readings(float* readings, const Body& T, const float (*obj)[3], const float* dist,
+                                                int leg, const DevConst& C) {
+  // ori = atan2 of the torso x-axis projected on xy: (q (0,1,0,0) q^-1)[1:3]
+  const float s = T.qw, x = T.qx, y = T.qy, z = T.qz;
+  // quat_mul(rot, (0,1,0,0)) = (-x, s, z, -y); times quat_inv(rot) = (s,-x,-y,-z)
+  const float aw = -x, ax = s, ay = z, az = -y;
+  const float ox = aw * (-x) + ax * s + ay * (-z) - az * (-y);
+  const float oy = aw * (-y) - ax * (-z) + ay * s + az * (-x);
+  const float ori = atan2f(oy, ox);
+  const int n_obj = C.n_apples + C.n_bombs, n_read = 2 * C.n_bins;
+  for (int turn = 0; turn < 4; ++turn) {
+    if (turn == leg) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kobj = 4 * leg + i;
+        if (kobj < n_obj) {
+          const float ang = __fsub_rn(atan2f(obj[i][0], obj[i][1]), ori);
+          const bool valid = (fabsf(ang) <= C.half_span) && (dist[i] <= C.sensor_range);
+          int bin = valid ? (int)__fdiv_rn(__fadd_rn(ang, C.half_span), C.bin_res) : -1;
+          if (kobj >= C.n_apples && bin >= 0) bin += C.n_apples;
+          const float inten = bin >= 0 ? __fsub_rn(1.0f, __fdiv_rn(dist[i], C.sensor_range)) : 0.0f;
+          if (bin < 0) bin += n_read;  // index -1 wraps to the last reading
+          if (bin < n_read) readings[bin] = inten;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Shared epilogue pieces ------------------------------------------------------------------------------
+// Coalesced write of the warp's 8 staged observation rows; where `from_first` the cached first_obs row.
+__device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, const float* __restrict__ first_obs,
+                                               const float* stage, int D, long long env0, int n_envs, unsigned first_mask,
+                                               unsigned skip_mask, int lane) {
+  for (int es = 0; es < 8; ++es) {
+    const long long e = env0 + es;
+    if (e >= n_envs) break;
+    if ((skip_mask >> es) & 1u) continue;
+    const bool ff = (first_mask >> es) & 1u;
+    float* dst = obs + e * D;
+    const float* src = stage + es * D;
+    const float* fsrc = first_obs + e * D;
+    for (int c = lane; c < D; c += 32) dst[c] = ff ? fsrc[c] : src[c];
+  }
+}
+
+// --------------------------------------------------------------------------------------------- step
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 4)
+step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float* __restrict__ action) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int leg = lane & 3, es = lane >> 2;
+  const int D = C.obs_dim;
+  const size_t n = (size_t)C.n_envs;
+  const long long env0 = ((long long)blockIdx.x * kEnvsPerBlock) + warp * 8;
+  const long long env_raw = env0 + es;
+  const bool valid = env_raw < (long long)n;
+  const size_t e = valid ? (size_t)env_raw : n - 1;  // out-of-range lanes shadow the last env (no stores)
+  float* stage = smem + (size_t)warp * 8 * D;
+  float* row = stage + es * D;
+
+  for (int i = lane; i < 8 * D; i += 32) stage[i] = 0.0f;
+
+  const LegK k = leg_consts(C, leg);
+  Rig r;
+  load_rig(reinterpret_cast<const float4*>(S.qp), n, e, leg, r);
+  const float2 act = reinterpret_cast<const float2*>(action)[e * 4 + leg];
+  float steps = S.steps[e];
+  const float done_prev = S.done[e];
+  if (C.auto_reset == POBRAX_AUTORESET_CACHED && done_prev != 0.0f) steps = 0.0f;  // AutoResetWrapper.step head
+  const float x_before = r.T.p.x;
+
+  Contact acc;
+  acc.Tv = acc.Tw = acc.Av = acc.Aw = acc.Bv = acc.Bw = mk(0.f, 0.f, 0.f);
+  if (KIND != POBRAX_ANT && C.n_walls > 0) {
+#pragma unroll 1
+    for (int s = 0; s < C.substeps; ++s) substep<true>(r, k, act.x, act.y, C, acc);
+  } else {
+#pragma unroll 1
+    for (int s = 0; s < C.substeps; ++s) substep<false>(r, k, act.x, act.y, C, acc);
+  }
+
+  __syncwarp();
+  stage_common_obs<KIND>(row, r, k, acc, leg, C);
+  const int extra = ObsCols<KIND>::cv + 6 * C.nb;
+
+  // ---- task logic (computed redundantly by the 4 lanes from the replicated torso; lane 0 stores)
+  const float tz = r.T.p.z;
+  float dead = tz < 0.2f ? 1.0f : 0.0f;
+  dead = tz > 1.0f ? 1.0f : dead;
+  float reward = 0.0f, done = 0.0f, m0 = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
+  double ev0 = 0.0, ev1 = 0.0, ev2 = 0.0;  // rare-event counters for acc[4..6]
+
+  if (KIND == POBRAX_ANT) {
+    const float forward = __fdiv_rn(__fsub_rn(r.T.p.x, x_before), C.dt);
+    const float ctrl = 0.5f * quad_sum(act.x * act.x + act.y * act.y);
+    auto sq3 = [](V3 v) { const float a = clip1(v.x), b = clip1(v.y), c = clip1(v.z); return a * a + b * b + c * c; };
+    const float contact = 0.5e-3f * (sq3(acc.Tv) + quad_sum(sq3(acc.Av) + sq3(acc.Bv)));
+    reward = ((forward - ctrl) - contact) + 1.0f;
+    done = dead;
+    m0 = ctrl; m1 = contact; m2 = forward; m3 = 1.0f;
+  } else if (KIND == POBRAX_ANT_HEAVENHELL) {
+    const int side = S.aux[2 * n + e] != 0.0f ? 1 : 0;
+    const float hx = C.hh_xy[side][0], hy = C.hh_xy[side][1];
+    const float lx = C.hh_xy[1 - side][0], ly = C.hh_xy[1 - side][1];
+    const bool in_heaven = norm2_rn(hx - r.T.p.x, hy - r.T.p.y) <= C.visible_radius;
+    const bool in_hell = norm2_rn(lx - r.T.p.x, ly - r.T.p.y) <= C.visible_radius;
+    const bool in_priest = norm2_rn(C.priest_xy[0] - r.T.p.x, C.priest_xy[1] - r.T.p.y) <= C.visible_radius;
+    reward = dead > 0.0f ? C.dying_cost : 0.0f;
+    reward = in_heaven ? 1.0f : reward;
+    reward = in_hell ? -1.0f : reward;
+    done = reward != 0.0f ? 1.0f : 0.0f;
+    m0 = done;
+    ev0 = done; ev1 = (reward == 1.0f); ev2 = (reward == -1.0f);
+    if (leg == 0) row[extra] = in_priest ? (hx > 0.0f ? 1.0f : (hx < 0.0f ? -1.0f : 0.0f)) : 0.0f;
+  } else if (KIND == POBRAX_ANT_TAG) {
+    // _step_target (ant_tag.py:129-146): rng, rng1 = split(rng); choice = randint(rng1, (), 0, 4)
+    Key key; key.k0 = S.rng[2 * e]; key.k1 = S.rng[2 * e + 1];
+    Key knext, k1;
+    split2(key, knext, k1);
+    const int choice = randint4(k1);
+    const float tx = S.aux[2 * n + e], ty = S.aux[3 * n + e];
+    float vx = __fsub_rn(r.T.p.x, tx), vy = __fsub_rn(r.T.p.y, ty);
+    const float nv = norm2_rn(vx, vy);
+    vx = __fdiv_rn(vx, nv); vy = __fdiv_rn(vy, nv);
+    float cx, cy;
+    if (choice == 0) { cx = vy; cy = -vx; }
+    else if (choice == 1) { cx = -vy; cy = vx; }
+    else if (choice == 2) { cx = -vx; cy = -vy; }
+    else { cx = 0.0f; cy = 0.0f; }
+    float nx = __fadd_rn(__fmul_rn(cx, C.target_step), tx), ny = __fadd_rn(__fmul_rn(cy, C.target_step), ty);
+    // (|new| > cage).any() -> keep the old position (NaN compares false, like the reference)
+    if (fabsf(nx) > C.cage_xy[0] || fabsf(ny) > C.cage_xy[1]) { nx = tx; ny = ty; }
+    const float dist = norm2_rn(__fsub_rn(nx, r.T.p.x), __fsub_rn(ny, r.T.p.y));
+    const bool vis = dist <= C.visible_radius;
+    const float hit = norm2_rn(__fsub_rn(r.T.p.x, nx), __fsub_rn(r.T.p.y, ny)) <= C.tag_radius ? 1.0f : 0.0f;
+    reward = dead > 0.0f ? C.dying_cost : 0.0f;
+    reward = hit > 0.0f ? 1.0f : reward;
+    done = (dead > 0.0f || hit > 0.0f) ? 1.0f : 0.0f;
+    m0 = hit;
+    ev0 = hit;
+    if (leg == 0) {
+      row[extra] = vis ? nx : 0.0f;
+      row[extra + 1] = vis ? ny : 0.0f;
+      if (valid) {
+        S.rng[2 * e] = knext.k0; S.rng[2 * e + 1] = knext.k1;
+        S.aux[2 * n + e] = nx; S.aux[3 * n + e] = ny; S.aux[4 * n + e] = 1.0f;
+      }
+    }
+  } else {  // POBRAX_ANT_GATHER
+    const int n_obj = C.n_apples + C.n_bombs;
+    float obj[4][3], dist[4];
+    int caught_a = 0, caught_b = 0, all_wait = 1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ko = 4 * leg + i;
+      if (ko < n_obj) {
+        obj[i][0] = S.aux[(size_t)(3 * ko) * n + e];
+        obj[i][1] = S.aux[(size_t)(3 * ko + 1) * n + e];
+        obj[i][2] = S.aux[(size_t)(3 * ko + 2) * n + e];
+        dist[i] = norm2_rn(__fsub_rn(r.T.p.x, obj[i][0]), __fsub_rn(r.T.p.y, obj[i][1]));
+      } else {
+        obj[i][0] = obj[i][1] = obj[i][2] = 0.0f; dist[i] = CUDART_INF_F;
+      }
+    }
+    __syncwarp();
+    gather_readings(row + extra, r.T, obj, dist, leg, C);  // obs uses the pre-pickup object positions
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ko = 4 * leg + i;
+      if (ko < n_obj) {
+        const bool in = dist[i] <= C.catch_range;
+        if (in) {
+          if (ko < C.n_apples) ++caught_a; else ++caught_b;
+          obj[i][0] = C.waiting[0]; obj[i][1] = C.waiting[1]; obj[i][2] = C.waiting[2];
+          if (valid) {
+            S.aux[(size_t)(3 * ko) * n + e] = obj[i][0];
+            S.aux[(size_t)(3 * ko + 1) * n + e] = obj[i][1];
+            S.aux[(size_t)(3 * ko + 2) * n + e] = obj[i][2];
+          }
+        }
+        all_wait &= (obj[i][0] == C.waiting[0] && obj[i][1] == C.waiting[1] && obj[i][2] == C.waiting[2]) ? 1 : 0;
+      }
+    }
+    caught_a = quad_isum(caught_a); caught_b = quad_isum(caught_b); all_wait = quad_and(all_wait);
+    reward = dead > 0.0f ? C.dying_cost : 0.0f;
+    reward = (caught_a > 0 && dead == 0.0f) ? 1.0f : reward;
+    reward = (caught_b > 0 && dead == 0.0f) ? -1.0f : reward;
+    done = all_wait ? 1.0f : dead;
+    m0 = (float)caught_a; m1 = (float)caught_b;
+    ev0 = caught_a; ev1 = caught_b;
+  }
+
+  // ---- brax EpisodeWrapper (episode_length, action_repeat 1): steps += 1; truncation; done at the limit
+  float trunc = 0.0f;
+  steps += 1.0f;
+  if (C.episode_length > 0 && steps >= (float)C.episode_length) {
+    trunc = 1.0f - done;
+    done = 1.0f;
+  }
+  const bool reset_now = (C.auto_reset == POBRAX_AUTORESET_CACHED) && done != 0.0f;
+
+  if (valid && leg == 0) {
+    S.reward[e] = reward;
+    S.done[e] = done;
+    S.steps[e] = steps;
+    S.truncation[e] = trunc;
+    if (C.metrics_dim > 0) S.metrics[e] = m0;
+    if (C.metrics_dim > 1) S.metrics[n + e] = m1;
+    if (C.metrics_dim > 2) S.metrics[2 * n + e] = m2;
+    if (C.metrics_dim > 3) S.metrics[3 * n + e] = m3;
+    if (C.track_metrics) {
+      const float ret = S.ep_return[e] + reward;
+      S.ep_return[e] = done != 0.0f ? 0.0f : ret;
+      if (done != 0.0f) {
+        atomicAdd(S.acc + 0, 1.0);
+        atomicAdd(S.acc + 1, (double)ret);
+        atomicAdd(S.acc + 2, (double)steps);
+        if (trunc != 0.0f) atomicAdd(S.acc + 3, 1.0);
+      }
+      if (ev0 != 0.0) atomicAdd(S.acc + 4, ev0);
+      if (ev1 != 0.0) atomicAdd(S.acc + 5, ev1);
+      if (ev2 != 0.0) atomicAdd(S.acc + 6, ev2);
+      if (dead != 0.0f) atomicAdd(S.acc + 7, 1.0);
+    }
+  }
+
+  // ---- brax AutoResetWrapper tail: qp/obs <- first_qp/first_obs where done
+  if (reset_now) {
+    load_rig(reinterpret_cast<const float4*>(S.first_qp), n, e, leg, r);
+    if (valid) {
+      for (int a = leg; a < C.aux_dim; a += 4) S.aux[(size_t)a * n + e] = S.first_aux[(size_t)a * n + e];
+    }
+  }
+  if (valid) store_rig(reinterpret_cast<float4*>(S.qp), n, e, leg, r);
+  const unsigned first_mask = __ballot_sync(kFull, reset_now && leg == 0);
+  unsigned fm8 = 0;
+  for (int i = 0; i < 8; ++i) fm8 |= ((first_mask >> (4 * i)) & 1u) << i;
+  __syncwarp();
+  write_obs_rows(S.obs, S.first_obs, stage, D, env0, C.n_envs, fm8, 0u, lane);
+}
+
+// -------------------------------------------------------------------------------------------- reset
+// quat_mul (Hamilton), used only by default_qp
+__device__ __forceinline__ void qmul(const float* u, const float* v, float* o) {
+  o[0] = u[0] * v[0] - u[1] * v[1] - u[2] * v[2] - u[3] * v[3];
+  o[1] = u[0] * v[1] + u[1] * v[0] + u[2] * v[3] - u[3] * v[2];
+  o[2] = u[0] * v[2] - u[1] * v[3] + u[2] * v[0] + u[3] * v[1];
+  o[3] = u[0] * v[3] + u[1] * v[2] - u[2] * v[1] + u[3] * v[0];
+}
+__device__ __forceinline__ V3 qrot(V3 v, const float* q) {
+  Body b; b.qw = q[0]; b.qx = q[1]; b.qy = q[2]; b.qz = q[3];
+  const Cols c = rot_cols(b);
+  return v.x * c.c0 + v.y * c.c1 + v.z * c.c2;
+}
+
+// System.default_qp for the lane's leg, torso at the origin, before the z-lift.
+__device__ __forceinline__ void default_leg(Rig& r, const LegK& k, float qh, float qa, float vh, float va,
+                                            const DevConst& C) {
+  r.T.p = mk(0.f, 0.f, 0.f); r.T.qw = 1.f; r.T.qx = r.T.qy = r.T.qz = 0.f;
+  r.T.v = r.T.w = mk(0.f, 0.f, 0.f);
+  // hip: axis e_z, parent = identity torso
+  float sh, ch; sincosf(0.5f * qh, &sh, &ch);
+  const float qA[4] = {ch, 0.f, 0.f, sh};
+  const V3 offp_h = mk(C.s_hip_p * k.ux, C.s_hip_p * k.uy, 0.f), offc_h = mk(C.s_hip_c * k.ux, C.s_hip_c * k.uy, 0.f);
+  r.A.p = offp_h - qrot(offc_h, qA);
+  r.A.qw = qA[0]; r.A.qx = qA[1]; r.A.qy = qA[2]; r.A.qz = qA[3];
+  r.A.v = mk(0.f, 0.f, 0.f);
+  r.A.w = mk(0.f, 0.f, vh);
+  // ankle: axis (cos phi, sin phi, 0) in the Aux frame
+  float sa, ca; sincosf(0.5f * qa, &sa, &ca);
+  const float ql[4] = {ca, k.axc * sa, k.axs * sa, 0.f};
+  float qB[4];
+  qmul(qA, ql, qB);
+  const V3 offp_a = mk(C.s_ank_p * k.ux, C.s_ank_p * k.uy, 0.f), offc_a = mk(C.s_ank_c * k.ux, C.s_ank_c * k.uy, 0.f);
+  r.B.p = r.A.p + qrot(offp_a - qrot(offc_a, ql), qA);
+  r.B.qw = qB[0]; r.B.qx = qB[1]; r.B.qy = qB[2]; r.B.qz = qB[3];
+  r.B.v = mk(0.f, 0.f, 0.f);
+  r.B.w = qrot(mk(k.axc * va, k.axs * va, 0.f), qA);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 2)
+reset_kernel(const __grid_constant__ DevConst C, const PobraxState S, const uint32_t* __restrict__ keys,
+             const float2* __restrict__ grid_xy, int only_done) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int leg = lane & 3, es = lane >> 2;
+  const int D = C.obs_dim;
+  const size_t n = (size_t)C.n_envs;
+  const long long env0 = ((long long)blockIdx.x * kEnvsPerBlock) + warp * 8;
+  const long long env_raw = env0 + es;
+  const bool valid = env_raw < (long long)n;
+  const size_t e = valid ? (size_t)env_raw : n - 1;
+  float* stage = smem + (size_t)warp * 8 * D;
+  float* row = stage + es * D;
+  uint32_t* sort_keys = reinterpret_cast<uint32_t*>(smem + (size_t)(kThreads / 32) * 8 * D) +
+                        (size_t)(warp * 8 + es) * (KIND == POBRAX_ANT_GATHER ? C.n_grid : 0);
+  for (int i = lane; i < 8 * D; i += 32) stage[i] = 0.0f;
+
+  const bool active = !only_done || S.done[e] != 0.0f;  // uniform over the quad
+  const LegK k = leg_consts(C, leg);
+  Key key; key.k0 = keys[2 * e]; key.k1 = keys[2 * e + 1];
+  constexpr int NSPLIT = (KIND == POBRAX_ANT) ? 3 : (KIND == POBRAX_ANT_GATHER ? 4 : 5);
+  const Key rng0 = split_at(key, NSPLIT, 0), r1 = split_at(key, NSPLIT, 1), r2 = split_at(key, NSPLIT, 2);
+  Key r3 = rng0, r4 = rng0;
+  if (KIND != POBRAX_ANT) r3 = split_at(key, NSPLIT, 3);
+  if (KIND == POBRAX_ANT_TAG) r4 = split_at(key, NSPLIT, 4);
+
+  // joint samples: default_angle + U(rng1, 8, -.1, .1), U(rng2, 8, -.1, .1)
+  const float qh = __fadd_rn(C.hip_default, uniform_rn(random_bits_at(r1, 8, 2 * leg), -0.1f, 0.1f));
+  const float qa = __fadd_rn(C.ank_default[leg], uniform_rn(random_bits_at(r1, 8, 2 * leg + 1), -0.1f, 0.1f));
+  const float vh = uniform_rn(random_bits_at(r2, 8, 2 * leg), -0.1f, 0.1f);
+  const float va = uniform_rn(random_bits_at(r2, 8, 2 * leg + 1), -0.1f, 0.1f);
+  Rig r;
+  default_leg(r, k, qh, qa, vh, va, C);
+  // z-lift: lowest collider point of the tree (torso sphere, both Aux end spheres, the foot end) to z = 0
+  {
+    const Cols cA = rot_cols(r.A), cB = rot_cols(r.B);
+    const V3 dA = k.ux * cA.c0 + k.uy * cA.c1, dB = k.ux * cB.c0 + k.uy * cB.c1;
+    float mz = (0.0f + 0.0f) - C.r_torso;
+    mz = fminf(mz, (r.A.p.z + C.s_aux * dA.z) - C.r_leg);
+    mz = fminf(mz, (r.A.p.z - C.s_aux * dA.z) - C.r_leg);
+    mz = fminf(mz, (r.B.p.z + C.s_foot * dB.z) - C.r_leg);
+    mz = quad_min(mz);
+    r.T.p.z -= mz; r.A.p.z -= mz; r.B.p.z -= mz;
+  }
+
+  // ---- task placement
+  float gx = 0.0f, gy = 0.0f;  // ant xy offset (added to the ant parts AND the Ground body)
+  float aux2 = 0.0f, aux3 = 0.0f, aux4 = 0.0f;
+  Key info_rng = rng0;
+  if (KIND == POBRAX_ANT_HEAVENHELL) {
+    gx = uniform_rn(random_bits_at(r3, 2, 0), C.init_lo[0], C.init_hi[0]);
+    gy = uniform_rn(random_bits_at(r3, 2, 1), C.init_lo[1], C.init_hi[1]);
+    // choice(rng3, hhp[:2], (2,), replace=False): one shuffle round = stable sort by bits(split(rng3)[1], 2)
+    Key a, b;
+    split2(r3, a, b);
+    const uint32_t s0 = random_bits_at(b, 2, 0), s1 = random_bits_at(b, 2, 1);
+    aux2 = (s0 <= s1) ? 0.0f : 1.0f;
+  } else if (KIND == POBRAX_ANT_TAG) {
+    gx = uniform_rn(random_bits_at(r3, 2, 0), -C.cage_xy[0], C.cage_xy[0]);
+    gy = uniform_rn(random_bits_at(r3, 2, 1), -C.cage_xy[1], C.cage_xy[1]);
+    // _random_target (ant_tag.py:90-105): rejection loop on the key chain k <- split(k)[1]
+    Key kk = r4;
+    float tx = uniform_rn(random_bits_at(kk, 2, 0), -C.cage_xy[0], C.cage_xy[0]);
+    float ty = uniform_rn(random_bits_at(kk, 2, 1), -C.cage_xy[1], C.cage_xy[1]);
+    if (active) {
+      while (norm2_rn(__fsub_rn(tx, gx), __fsub_rn(ty, gy)) <= C.min_spawn) {
+        Key a, b;
+        split2(kk, a, b);
+        kk = b;
+        tx = uniform_rn(random_bits_at(kk, 2, 0), -C.cage_xy[0], C.cage_xy[0]);
+        ty = uniform_rn(random_bits_at(kk, 2, 1), -C.cage_xy[1], C.cage_xy[1]);
+      }
+    }
+    aux2 = tx; aux3 = ty; aux4 = 0.5f;
+  } else if (KIND == POBRAX_ANT_GATHER) {
+    info_rng = key;  // ant_gather.py:106 keeps the un-split input key
+  }
+  r.T.p.x += gx; r.T.p.y += gy;
+  r.A.p.x += gx; r.A.p.y += gy;
+  r.B.p.x += gx; r.B.p.y += gy;
+
+  float obj[4][3], dist[4];
+  if (KIND == POBRAX_ANT_GATHER) {
+    // choice(rng3, grid, (n_objects,), replace=False) = grid[stable_argsort(bits(split(rng3)[1], n_grid))[:n_objects]]
+    const int n_obj = C.n_apples + C.n_bombs, ng = C.n_grid;
+    Key a, b;
+    split2(r3, a, b);
+    for (int i = leg; i < ng; i += 4) sort_keys[i] = random_bits_at(b, ng, i);
+    __syncwarp();
+    // selection of the n_obj smallest (key, index) pairs in order; each lane scans a quarter
+    uint32_t pk = 0; int pi = -1;
+    for (int j = 0; j < n_obj; ++j) {
+      uint32_t bk = 0xffffffffu; int bi = 0x7fffffff;
+      for (int i = leg; i < ng; i += 4) {
+        const uint32_t kv = sort_keys[i];
+        const bool after_prev = (pi < 0) || kv > pk || (kv == pk && i > pi);
+        const bool better = kv < bk || (kv == bk && i < bi);
+        if (after_prev && better) { bk = kv; bi = i; }
+      }
+#pragma unroll
+      for (int m = 1; m <= 2; m <<= 1) {
+        const uint32_t ok = __shfl_xor_sync(kFull, bk, m);
+        const int oi = __shfl_xor_sync(kFull, bi, m);
+        if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+      }
+      pk = bk; pi = bi;
+      if ((j >> 2) == leg) {
+        const float2 g = grid_xy[bi];
+        const int i = j & 3;
+        obj[i][0] = g.x; obj[i][1] = g.y; obj[i][2] = j < C.n_apples ? 1.0f : 0.0f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (4 * leg + i < n_obj) {
+        dist[i] = norm2_rn(__fsub_rn(r.T.p.x, obj[i][0]), __fsub_rn(r.T.p.y, obj[i][1]));
+      } else {
+        obj[i][0] = obj[i][1] = obj[i][2] = 0.0f; dist[i] = CUDART_INF_F;
+      }
+    }
+  }
+
+  // ---- info = sys.info(qp): one collider evaluation, no integration
+  Contact ct;
+  {
+    const Cols cA = rot_cols(r.A), cB = rot_cols(r.B);
+    const V3 dA = k.ux * cA.c0 + k.uy * cA.c1, dB = k.ux * cB.c0 + k.uy * cB.c1;
+    if (KIND != POBRAX_ANT && C.n_walls > 0) contacts<true>(r, k, C, dA, dB, ct);
+    else contacts<false>(r, k, C, dA, dB, ct);
+  }
+  __syncwarp();
+  stage_common_obs<KIND>(row, r, k, ct, leg, C);
+  const int extra = ObsCols<KIND>::cv + 6 * C.nb;
+  if (KIND == POBRAX_ANT_TAG) {
+    const bool vis = norm2_rn(__fsub_rn(aux2, r.T.p.x), __fsub_rn(aux3, r.T.p.y)) <= C.visible_radius;
+    if (leg == 0) { row[extra] = vis ? aux2 : 0.0f; row[extra + 1] = vis ? aux3 : 0.0f; }
+  } else if (KIND == POBRAX_ANT_GATHER) {
+    __syncwarp();
+    gather_readings(row + extra, r.T, obj, dist, leg, C);
+  }  // HeavenHell: heaven_direction = 0 at reset (ant_heavenhell.py:78)
+
+  // ---- stores
+  const bool wr = valid && active;
+  if (wr) {
+    store_rig(reinterpret_cast<float4*>(S.qp), n, e, leg, r);
+    if (!only_done && S.first_qp) store_rig(reinterpret_cast<float4*>(S.first_qp), n, e, leg, r);
+    if (KIND == POBRAX_ANT_GATHER) {
+      const int n_obj = C.n_apples + C.n_bombs;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ko = 4 * leg + i;
+        if (ko < n_obj) {
+          for (int c = 0; c < 3; ++c) {
+            S.aux[(size_t)(3 * ko + c) * n + e] = obj[i][c];
+            if (!only_done && S.first_aux) S.first_aux[(size_t)(3 * ko + c) * n + e] = obj[i][c];
+          }
+        }
+      }
+    }
+    if (leg == 0) {
+      if (KIND == POBRAX_ANT_HEAVENHELL || KIND == POBRAX_ANT_TAG) {
+        const float av[5] = {gx, gy, aux2, aux3, aux4};
+        for (int a = 0; a < C.aux_dim; ++a) {
+          S.aux[(size_t)a * n + e] = av[a];
+          if (!only_done && S.first_aux) S.first_aux[(size_t)a * n + e] = av[a];
+        }
+      }
+      S.steps[e] = 0.0f;
+      if (!only_done) {
+        S.reward[e] = 0.0f; S.done[e] = 0.0f; S.truncation[e] = 0.0f;
+        for (int m = 0; m < C.metrics_dim; ++m) S.metrics[(size_t)m * n + e] = 0.0f;
+        if (C.has_rng) { S.rng[2 * e] = info_rng.k0; S.rng[2 * e + 1] = info_rng.k1; }
+        if (S.ep_return) S.ep_return[e] = 0.0f;
+      }
+    }
+  }
+  const unsigned skip = __ballot_sync(kFull, !active && leg == 0);
+  unsigned sk8 = 0;
+  for (int i = 0; i < 8; ++i) sk8 |= ((skip >> (4 * i)) & 1u) << i;
+  __syncwarp();
+  write_obs_rows(S.obs, S.obs, stage, D, env0, C.n_envs, 0u, sk8, lane);
+  if (!only_done && S.first_obs) write_obs_rows(S.first_obs, S.obs, stage, D, env0, C.n_envs, 0u, sk8, lane);
+}
+
+// --------------------------------------------------------------------------- brax.QP <-> packed state
+// One thread per (env, body): pos[N][nb][3], rot[N][nb][4], vel[N][nb][3], ang[N][nb][3].
+__device__ __forceinline__ float packed_get(const float* qp, size_t n, size_t e, int body, int f) {
+  // f: 0..12 = px py pz qw qx qy qz vx vy vz wx wy wz of ant body 0..8
+  int plane, comp;
+  if (body == 0) { plane = f >> 2; comp = f & 3; }
+  else {
+    const int leg = (body - 1) >> 1, lower = (body - 1) & 1;
+    const int idx = lower ? 13 + f : f;
+    plane = 4 + 7 * leg + (idx >> 2); comp = idx & 3;
+  }
+  return qp[((size_t)plane * n + e) * 4 + comp];
+}
+__device__ __forceinline__ void packed_set(float* qp, size_t n, size_t e, int body, int f, float v) {
+  int plane, comp;
+  if (body == 0) { plane = f >> 2; comp = f & 3; }
+  else {
+    const int leg = (body - 1) >> 1, lower = (body - 1) & 1;
+    const int idx = lower ? 13 + f : f;
+    plane = 4 + 7 * leg + (idx >> 2); comp = idx & 3;
+  }
+  qp[((size_t)plane * n + e) * 4 + comp] = v;
+}
+
+__global__ void unpack_qp_kernel(const __grid_constant__ DevConst C, const float* __restrict__ qp,
+                                 const float* __restrict__ aux, float* __restrict__ pos, float* __restrict__ rot,
+                                 float* __restrict__ vel, float* __restrict__ ang) {
+  const size_t n = (size_t)C.n_envs;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * C.nb) return;
+  const size_t e = t / C.nb;
+  const int b = (int)(t % C.nb);
+  float f[13] = {0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (b < 9) {
+    for (int i = 0; i < 13; ++i) f[i] = packed_get(qp, n, e, b, i);
+  } else if (b == 9) {  // Ground: xy follows the ant's spawn offset (HeavenHell / Tag)
+    if (C.env_kind == POBRAX_ANT_HEAVENHELL || C.env_kind == POBRAX_ANT_TAG) { f[0] = aux[e]; f[1] = aux[n + e]; }
+  } else if (C.env_kind == POBRAX_ANT_HEAVENHELL) {
+    const int side = aux[2 * n + e] != 0.0f ? 1 : 0;
+    if (b == 10) { f[0] = C.priest_xy[0]; f[1] = C.priest_xy[1]; f[2] = C.priest_z; }
+    else if (b == 11) { f[0] = C.hh_xy[side][0]; f[1] = C.hh_xy[side][1]; f[2] = C.hh_z; }
+    else if (b == 12) { f[0] = C.hh_xy[1 - side][0]; f[1] = C.hh_xy[1 - side][1]; f[2] = C.hh_z; }
+    else { f[2] = C.arena_z; }
+  } else if (C.env_kind == POBRAX_ANT_TAG) {
+    if (b == 10) { f[0] = aux[2 * n + e]; f[1] = aux[3 * n + e]; f[2] = aux[4 * n + e]; }
+    else { f[2] = C.arena_z; }
+  } else if (C.env_kind == POBRAX_ANT_GATHER) {
+    if (b == 10) { f[2] = C.arena_z; }
+    else { const int ko = b - 11; for (int c = 0; c < 3; ++c) f[c] = aux[(size_t)(3 * ko + c) * n + e]; }
+  }
+  for (int c = 0; c < 3; ++c) { pos[t * 3 + c] = f[c]; vel[t * 3 + c] = f[7 + c]; ang[t * 3 + c] = f[10 + c]; }
+  for (int c = 0; c < 4; ++c) rot[t * 4 + c] = f[3 + c];
+}
+
+__global__ void pack_qp_kernel(const __grid_constant__ DevConst C, const float* __restrict__ pos,
+                               const float* __restrict__ rot, const float* __restrict__ vel,
+                               const float* __restrict__ ang, float* __restrict__ qp, float* __restrict__ aux) {
+  const size_t n = (size_t)C.n_envs;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * C.nb) return;
+  const size_t e = t / C.nb;
+  const int b = (int)(t % C.nb);
+  if (b < 9) {
+    for (int c = 0; c < 3; ++c) {
+      packed_set(qp, n, e, b, c, pos[t * 3 + c]);
+      packed_set(qp, n, e, b, 7 + c, vel[t * 3 + c]);
+      packed_set(qp, n, e, b, 10 + c, ang[t * 3 + c]);
+    }
+    for (int c = 0; c < 4; ++c) packed_set(qp, n, e, b, 3 + c, rot[t * 4 + c]);
+    if (b == 0) {  // torso plane 3 padding
+      qp[((size_t)3 * n + e) * 4 + 1] = 0.f; qp[((size_t)3 * n + e) * 4 + 2] = 0.f; qp[((size_t)3 * n + e) * 4 + 3] = 0.f;
+    } else if (((b - 1) & 1) == 1) {
+      const int leg = (b - 1) >> 1;
+      qp[((size_t)(4 + 7 * leg + 6) * n + e) * 4 + 2] = 0.f; qp[((size_t)(4 + 7 * leg + 6) * n + e) * 4 + 3] = 0.f;
+    }
+  } else if (b == 9) {
+    if (C.env_kind == POBRAX_ANT_HEAVENHELL || C.env_kind == POBRAX_ANT_TAG) { aux[e] = pos[t * 3]; aux[n + e] = pos[t * 3 + 1]; }
+  } else if (C.env_kind == POBRAX_ANT_HEAVENHELL) {
+    if (b == 11) aux[2 * n + e] = (pos[t * 3] == C.hh_xy[1][0] && pos[t * 3 + 1] == C.hh_xy[1][1] &&
+                                   !(C.hh_xy[0][0] == C.hh_xy[1][0] && C.hh_xy[0][1] == C.hh_xy[1][1])) ? 1.0f : 0.0f;
+  } else if (C.env_kind == POBRAX_ANT_TAG) {
+    if (b == 10) { aux[2 * n + e] = pos[t * 3]; aux[3 * n + e] = pos[t * 3 + 1]; aux[4 * n + e] = pos[t * 3 + 2]; }
+  } else if (C.env_kind == POBRAX_ANT_GATHER) {
+    if (b >= 11) { const int ko = b - 11; for (int c = 0; c < 3; ++c) aux[(size_t)(3 * ko + c) * n + e] = pos[t * 3 + c]; }
+  }
+}
+
+// jax.random.split(key, n)[first : first + count] (counter based: any slice is local work)
+__global__ void split_keys_kernel(Key key, int n, int first, int count, uint32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const Key k = split_at(key, n, first + i);
+  out[2 * i] = k.k0;
+  out[2 * i + 1] = k.k1;
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+static size_t obs_stage_bytes(const DevConst& C) { return (size_t)(kThreads / 32) * 8 * C.obs_dim * sizeof(float); }
+
+template <int KIND>
+static cudaError_t launch_step_t(const DevConst& C, const PobraxState& S, const float* action, cudaStream_t st) {
+  const size_t smem = obs_stage_bytes(C);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(step_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_set = true;
+  }
+  const int blocks = (C.n_envs + kEnvsPerBlock - 1) / kEnvsPerBlock;
+  step_kernel<KIND><<<blocks, kThreads, smem, st>>>(C, S, action);
+  return cudaGetLastError();
+}
+
+template <int KIND>
+static cudaError_t launch_reset_t(const DevConst& C, const PobraxState& S, const uint32_t* keys, const float2* grid,
+                                  int only_done, cudaStream_t st) {
+  size_t smem = obs_stage_bytes(C);
+  if (KIND == POBRAX_ANT_GATHER) smem += (size_t)kEnvsPerBlock * C.n_grid * sizeof(uint32_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(reset_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_set = true;
+  }
+  const int blocks = (C.n_envs + kEnvsPerBlock - 1) / kEnvsPerBlock;
+  reset_kernel<KIND><<<blocks, kThreads, smem, st>>>(C, S, keys, grid, only_done);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_step(const DevConst& C, const PobraxState& S, const float* action, cudaStream_t st) {
+  switch (C.env_kind) {
+    case POBRAX_ANT: return launch_step_t<POBRAX_ANT>(C, S, action, st);
+    case POBRAX_ANT_HEAVENHELL: return launch_step_t<POBRAX_ANT_HEAVENHELL>(C, S, action, st);
+    case POBRAX_ANT_GATHER: return launch_step_t<POBRAX_ANT_GATHER>(C, S, action, st);
+    case POBRAX_ANT_TAG: return launch_step_t<POBRAX_ANT_TAG>(C, S, action, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_reset(const DevConst& C, const PobraxState& S, const uint32_t* keys, const float2* grid,
+                         int only_done, cudaStream_t st) {
+  switch (C.env_kind) {
+    case POBRAX_ANT: return launch_reset_t<POBRAX_ANT>(C, S, keys, grid, only_done, st);
+    case POBRAX_ANT_HEAVENHELL: return launch_reset_t<POBRAX_ANT_HEAVENHELL>(C, S, keys, grid, only_done, st);
+    case POBRAX_ANT_GATHER: return launch_reset_t<POBRAX_ANT_GATHER>(C, S, keys, grid, only_done, st);
+    case POBRAX_ANT_TAG: return launch_reset_t<POBRAX_ANT_TAG>(C, S, keys, grid, only_done, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_unpack(const DevConst& C, const float* qp, const float* aux, float* pos, float* rot, float* vel,
+                          float* ang, cudaStream_t st) {
+  const size_t total = (size_t)C.n_envs * C.nb;
+  unpack_qp_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(C, qp, aux, pos, rot, vel, ang);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack(const DevConst& C, const float* pos, const float* rot, const float* vel, const float* ang,
+                        float* qp, float* aux, cudaStream_t st) {
+  const size_t total = (size_t)C.n_envs * C.nb;
+  pack_qp_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(C, pos, rot, vel, ang, qp, aux);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_split_keys(const uint32_t key[2], int n, int first, int count, uint32_t* out, cudaStream_t st) {
+  Key k; k.k0 = key[0]; k.k1 = key[1];
+  if (count <= 0) return cudaSuccess;
+  split_keys_kernel<<<(count + 255) / 256, 256, 0, st>>>(k, n, first, count, out);
+  return cudaGetLastError();
+}
+
+}  // namespace pobrax
+
+// ------------------------------------------------------------------------- FP32 FMA peak probe (bench)
+// 8 independent FMA chains per thread; used by bench.py to measure the non-tensor FP32 roof on the box.
+namespace pobrax {
+__global__ void __launch_bounds__(256) fma_probe_kernel(float* __restrict__ out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // keep the chains alive
+}
+cudaError_t launch_fma_probe(float* out, int blocks, int iters, cudaStream_t st) {
+  fma_probe_kernel<<<blocks, 256, 0, st>>>(out, iters, 0.999f, 0.001f);
+  return cudaGetLastError();
+}
+}  // namespace pobrax

@@ -1,0 +1,78 @@
+"""Shared helpers for the GPU parity tests: oracle <-> CUDA state conversion and tolerances.
+
+Tolerances (stated here once, used by every parity test):
+  * integers / RNG bits / done flags / item indices: bit-exact.
+  * pos, rot, joint angles (teacher-forced, one env step from identical states): |d| <= 1e-6 + 2e-6*|x|
+    -- SURVEY App. C gate; the float32 oracle itself is 8e-7 (pos) / 4e-7 (rot) away from its float64 twin.
+  * vel, ang, joint velocities, contact impulses: |d| <= 3e-4 -- the stiff joint springs (k = 18000, h = 5 ms)
+    amplify float32 rounding of positions: the float32 oracle is up to 1.1e-4 away from the float64 oracle
+    after one step (measured over 60 steps x 256 envs), so 3e-4 is ~3x the reference arithmetic's own noise.
+"""
+import numpy as np
+import torch
+
+from oracle import brax_v1 as bx
+from oracle import envs as oenvs
+from oracle import threefry as tf
+
+POS_TOL = (1e-6, 2e-6)
+VEL_ATOL = 3e-4
+
+
+def keys_for(n, seed=0):
+    """VmapGymWrapper._reset key scheme (wrappers.py:160-163): split(PRNGKey(seed), n+1)[1:]."""
+    return tf.split(tf.prng_key(seed), n + 1)[1:]
+
+
+def actions_for(rng, n):
+    """BASELINE config 1: rng, k = split(rng); a = uniform(k, (n, 8), -1, 1)."""
+    ks = tf.split(rng, 2)
+    return ks[0], tf.uniform(ks[1], n * 8, -1.0, 1.0).reshape(n, 8)
+
+
+def t2n(x):
+    return x.detach().cpu().numpy()
+
+
+def rng_bits(t):
+    return t2n(t).view(np.uint32)
+
+
+def qp_to_torch(qp, device='cuda'):
+    from po_brax_b200.envs import QP
+    return QP(*[torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=device)
+                for a in (qp.pos, qp.rot, qp.vel, qp.ang)])
+
+
+def close_pos(a, b):
+    return np.abs(a - b) <= POS_TOL[0] + POS_TOL[1] * np.abs(b)
+
+
+def assert_qp_close(got, want, what='', vel_atol=VEL_ATOL):
+    for name, tight in (('pos', True), ('rot', True), ('vel', False), ('ang', False)):
+        g, w = t2n(getattr(got, name)), getattr(want, name)
+        ok = close_pos(g, w) if tight else (np.abs(g - w) <= vel_atol)
+        assert ok.all(), f'{what} qp.{name}: max |d| = {np.abs(g - w).max():.3e} at {np.argwhere(~ok)[:4].tolist()}'
+
+
+def obs_tolerances(kind, nb, obs_dim):
+    """Per-column absolute / relative tolerance of the observation."""
+    P = 1 if kind == 'ant' else 3
+    atol = np.full(obs_dim, VEL_ATOL, np.float64)
+    rtol = np.zeros(obs_dim, np.float64)
+    tight = list(range(0, P + 4))                 # torso pos, rot
+    atol[tight] = POS_TOL[0]
+    rtol[tight] = POS_TOL[1]
+    atol[P + 4:P + 12] = 5e-6                     # joint angles (atan2 of unit-vector products)
+    end = P + 26 + 6 * nb
+    atol[end:] = 1e-5                             # task extras (exact unless stated otherwise by the test)
+    return atol, rtol
+
+
+def assert_obs_close(got, want, kind, nb, what='', mask=None):
+    atol, rtol = obs_tolerances(kind, nb, want.shape[-1])
+    ok = np.abs(got - want) <= atol + rtol * np.abs(want)
+    if mask is not None:
+        ok = ok | ~mask
+    assert ok.all(), (f'{what} obs: {int((~ok).sum())} entries off, worst {np.abs(got - want)[~ok].max():.3e} at '
+                      f'{np.argwhere(~ok)[:6].tolist()}')

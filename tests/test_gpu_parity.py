@@ -1,0 +1,287 @@
+"""CUDA path vs the CPU oracle through the public env API (which calls the C-ABI via ctypes).
+Run on the B200 box: python -m pytest tests -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import envs as oenvs
+from oracle import threefry as tf
+from tests import _parity as P
+
+pytestmark = pytest.mark.gpu
+
+KINDS = ['ant', 'ant_heavenhell', 'ant_tag', 'ant_gather']
+
+
+def _make(kind, n, **kw):
+    from po_brax_b200 import envs
+    return envs.create(kind, batch_size=n, **kw)
+
+
+def _oracle_aux(kind, oenv, s):
+    """The per-env frozen-body data the CUDA path keeps in `aux`, from the oracle's full qp."""
+    if kind == 'ant_heavenhell':
+        return s.qp.pos[:, oenv.target_idx, 0]
+    if kind == 'ant_tag':
+        return s.qp.pos[:, oenv.target_idx]
+    if kind == 'ant_gather':
+        return s.qp.pos[:, oenv.obj]
+    return None
+
+
+@pytest.mark.parametrize('kind', KINDS)
+def test_reset_parity(kind):
+    n = 256
+    keys = P.keys_for(n, seed=0)
+    oenv = oenvs.ENVS[kind]()
+    want = oenv.reset(keys)
+    env = _make(kind, n)
+    got = env.reset(keys)
+    torch.cuda.synchronize()
+    nb = oenv.sys.num_bodies
+    assert env.observation_size == want.obs.shape[1] and env.num_bodies == nb
+    # integers / RNG: bit-exact
+    if kind != 'ant':
+        assert (P.rng_bits(got.info['rng']) == want.info['rng']).all()
+    gq = got.qp
+    if kind == 'ant_heavenhell':
+        assert (P.t2n(gq.pos)[:, oenv.target_idx] == want.qp.pos[:, oenv.target_idx]).all()  # heaven side
+        assert (P.t2n(gq.pos)[:, oenv.hell_idx] == want.qp.pos[:, oenv.hell_idx]).all()
+        assert (P.t2n(gq.pos)[:, oenv.priest_idx] == want.qp.pos[:, oenv.priest_idx]).all()
+    if kind == 'ant_tag':
+        assert (P.t2n(gq.pos)[:, oenv.target_idx] == want.qp.pos[:, oenv.target_idx]).all()  # rejection loop
+    if kind == 'ant_gather':
+        assert (P.t2n(gq.pos)[:, oenv.obj] == want.qp.pos[:, oenv.obj]).all()                # 16-of-156 choice
+    # every frozen body (Ground, Arena, Priest/Target/Hell, apples/bombs), exactly
+    assert np.array_equal(P.t2n(gq.pos)[:, 9:], want.qp.pos[:, 9:])
+    assert np.array_equal(P.t2n(gq.rot)[:, 9:], want.qp.rot[:, 9:])
+    P.assert_qp_close(gq, want.qp, f'{kind} reset')
+    # obs: the contact columns of a body resting exactly on z = 0 (|pen| ~ 1 ulp after the z-lift) flip with
+    # rounding in the reference itself; they are compared only where the oracle's penetration is unambiguous
+    gobs = P.t2n(got.obs)
+    mask = np.ones_like(want.obs, bool)
+    Pc = 1 if kind == 'ant' else 3
+    cv0 = Pc + 26
+    ambiguous = _ambiguous_contacts(oenv, want.qp)
+    for b in range(9):
+        cols = [cv0 + 3 * b + c for c in range(3)] + [cv0 + 3 * nb + 3 * b + c for c in range(3)]
+        mask[np.ix_(ambiguous[:, b], cols)] = False
+    P.assert_obs_close(gobs, want.obs, kind, nb, f'{kind} reset', mask=mask)
+    assert mask.mean() > 0.97
+    for name in ('reward', 'done'):
+        assert (P.t2n(getattr(got, name)) == 0).all()
+    assert (P.t2n(got.info['steps']) == 0).all()
+
+
+def _ambiguous_contacts(oenv, qp, eps=1e-5):
+    """[N, 9] bool: bodies with a ground-contact candidate whose |penetration| < eps (sign decided by rounding),
+    or (walls) a capsule within eps of touching a wall."""
+    from oracle import brax_v1 as bx
+    s = oenv.sys
+    n = qp.pos.shape[0]
+    amb = np.zeros((n, 9), bool)
+    b = s.cp_body
+    end_w = qp.pos[:, b] + bx.rotate(np.broadcast_to(s.cp_end, qp.pos[:, b].shape), qp.rot[:, b])
+    pen = -(end_w[..., 2] - s.cp_rad)
+    for k, body in enumerate(b):
+        amb[:, body] |= np.abs(pen[:, k]) < eps
+    if len(s.boxes):
+        nbx = len(s.boxes)
+        bb = np.repeat(s.cap_body, nbx)
+        ca, cb = np.repeat(s.cap_a, nbx, axis=0), np.repeat(s.cap_b, nbx, axis=0)
+        rad = np.repeat(s.cap_rad, nbx)
+        box = np.tile(s.boxes, (len(s.cap_body), 1))
+        pos, rot = qp.pos[:, bb], qp.rot[:, bb]
+        apos = qp.pos[:, s.arena][:, None, :]
+        a_w = pos + bx.rotate(np.broadcast_to(ca, pos.shape), rot)
+        b_w = pos + bx.rotate(np.broadcast_to(cb, pos.shape), rot)
+        sp, bp = s._closest_segment_box(a_w, b_w, apos + box[:, :3], apos + box[:, 3:])
+        d = np.sqrt(((sp - bp) ** 2).sum(-1))
+        near = np.abs(rad - d) < eps
+        for k, body in enumerate(bb):
+            amb[:, body] |= near[:, k]
+    return amb
+
+
+@pytest.mark.parametrize('kind', KINDS)
+def test_step_teacher_forced(kind):
+    """One env step from identical states, T times along an oracle rollout (BASELINE config 1 key scheme)."""
+    n, T = 128, 25
+    keys = P.keys_for(n, seed=0)
+    oenv = oenvs.ENVS[kind]()
+    nb = oenv.sys.num_bodies
+    s = oenv.reset(keys)
+    env = _make(kind, n, auto_reset=False, episode_length=1000)
+    rng = tf.prng_key(1)
+    worst = {}
+    for t in range(T):
+        rng, a = P.actions_for(rng, n)
+        cs = env.state_from_qp(P.qp_to_torch(s.qp), rng=s.info.get('rng'))
+        nxt = oenv.step(oenvs.State(s.qp.copy(), s.obs, s.reward, s.done, dict(s.metrics), dict(s.info)), a)
+        got = env.step(cs, torch.as_tensor(a, device='cuda'))
+        torch.cuda.synchronize()
+        P.assert_qp_close(got.qp, nxt.qp, f'{kind} t={t}')
+        assert np.array_equal(P.t2n(got.done), np.asarray(nxt.done, np.float32)), f'{kind} t={t} done'
+        if kind == 'ant':
+            assert np.abs(P.t2n(got.reward) - nxt.reward).max() <= 2e-3  # forward = dx / dt amplifies pos noise x20
+        else:
+            assert np.array_equal(P.t2n(got.reward), nxt.reward), f'{kind} t={t} reward'
+        if kind == 'ant_tag':
+            assert (P.rng_bits(got.info['rng']) == nxt.info['rng']).all()
+            assert np.array_equal(P.t2n(got.metrics['hits']), nxt.metrics['hits'])
+        if kind == 'ant_gather':
+            assert np.array_equal(P.t2n(got.metrics['apples']), nxt.metrics['apples'].astype(np.float32))
+            assert np.array_equal(P.t2n(got.metrics['bombs']), nxt.metrics['bombs'].astype(np.float32))
+        mask = None
+        if kind == 'ant_gather':  # a sensor bin index is int(trunc(angle / res)): exclude angles within 1e-5 of an edge
+            mask = np.ones_like(nxt.obs, bool)
+            mask[:, -2 * oenv.n_bins:] = _gather_reading_mask(oenv, nxt, got)
+        P.assert_obs_close(P.t2n(got.obs), nxt.obs, kind, nb, f'{kind} t={t}', mask=mask)
+        s = nxt
+        if kind != 'ant_tag':
+            s.info['rng'] = s.info.get('rng')
+
+
+def _gather_reading_mask(oenv, nxt, got):
+    g, w = P.t2n(got.obs)[:, -2 * oenv.n_bins:], nxt.obs[:, -2 * oenv.n_bins:]
+    ok = np.abs(g - w) <= 1e-5
+    # rows that differ are accepted only if they hold the same multiset of intensities shifted by one bin
+    bad_rows = ~ok.all(axis=1)
+    mask = np.ones_like(ok)
+    for r in np.nonzero(bad_rows)[0]:
+        if np.allclose(np.sort(g[r]), np.sort(w[r]), atol=1e-5):
+            mask[r] = False
+    assert bad_rows.mean() <= 0.01
+    return mask
+
+
+@pytest.mark.parametrize('kind', ['ant_heavenhell', 'ant_tag'])
+def test_free_running_20_steps(kind):
+    """Free-running rollout; SURVEY App. C gate: <= 3e-5 abs on pos/rot after 20 steps (chaos sets in later)."""
+    n, T = 64, 20
+    keys = P.keys_for(n, seed=3)
+    oenv = oenvs.ENVS[kind]()
+    s = oenv.reset(keys)
+    env = _make(kind, n, auto_reset=False)
+    cs = env.reset(keys)
+    rng = tf.prng_key(1)
+    for t in range(T):
+        rng, a = P.actions_for(rng, n)
+        s = oenv.step(s, a)
+        cs = env.step(cs, torch.as_tensor(a, device='cuda'))
+    q = cs.qp
+    # envs whose reset had a rounding-ambiguous contact start from (legitimately) different impulses
+    err = np.maximum(np.abs(P.t2n(q.pos)[:, :9] - s.qp.pos[:, :9]).reshape(n, -1).max(1),
+                     np.abs(P.t2n(q.rot)[:, :9] - s.qp.rot[:, :9]).reshape(n, -1).max(1))
+    assert np.quantile(err, 0.9) <= 3e-5, np.sort(err)[-8:]
+    assert np.median(err) <= 1e-5
+
+
+@pytest.mark.parametrize('kind', KINDS)
+def test_episode_and_cached_autoreset(kind):
+    """brax EpisodeWrapper + AutoResetWrapper semantics fused into the step kernel (create(auto_reset=True))."""
+    n, L, T = 64, 4, 11
+    keys = P.keys_for(n, seed=5)
+    oenv = oenvs.create(kind, episode_length=L, auto_reset=True)
+    s = oenv.reset(keys)
+    env = _make(kind, n, episode_length=L, auto_reset=True)
+    cs = env.reset(keys)
+    rng = tf.prng_key(2)
+    for t in range(T):
+        rng, a = P.actions_for(rng, n)
+        s = oenv.step(s, a)
+        cs = env.step(cs, torch.as_tensor(a, device='cuda'))
+        assert np.array_equal(P.t2n(cs.info['steps']), s.info['steps']), f't={t}'
+        assert np.array_equal(P.t2n(cs.done), np.asarray(s.done, np.float32)), f't={t}'
+        assert np.array_equal(P.t2n(cs.info['truncation']), s.info['truncation']), f't={t}'
+        # within an episode of 4 steps free-running drift stays far below the gates; after a reset both sides
+        # return to the cached first state
+        P.assert_qp_close(cs.qp, s.qp, f'{kind} autoreset t={t}', vel_atol=2e-3)
+    assert float(P.t2n(cs.done).sum()) >= 0
+
+
+@pytest.mark.parametrize('kind', ['ant_heavenhell', 'ant_gather', 'ant_tag'])
+def test_gym_reset_where_done(kind):
+    """wrappers.py:245-262: where done, qp/obs <- fresh reset(keys[i]); steps <- 0; everything else kept."""
+    n = 64
+    keys0, keys1 = P.keys_for(n, seed=7), P.keys_for(n, seed=8)
+    env = _make(kind, n, auto_reset=False, episode_length=3)
+    cs = env.reset(keys0)
+    a = torch.zeros((n, 8), device='cuda')
+    for _ in range(2):
+        cs = env.step(cs, a)
+    done = torch.zeros(n, device='cuda')
+    done[::3] = 1.0
+    cs.buf['done'].copy_(done)
+    before = {k: v.clone() for k, v in cs.buf.items() if v is not None}
+    fresh = env.reset(keys1)
+    cs = env.reset_where_done(cs, keys1)
+    torch.cuda.synchronize()
+    d = done.bool()
+    assert torch.equal(cs.buf['qp'][:, d], fresh.buf['qp'][:, d]) and torch.equal(cs.buf['qp'][:, ~d], before['qp'][:, ~d])
+    assert torch.equal(cs.obs[d], fresh.obs[d]) and torch.equal(cs.obs[~d], before['obs'][~d])
+    assert torch.equal(cs.buf['aux'][:, d], fresh.buf['aux'][:, d]) and torch.equal(cs.buf['aux'][:, ~d], before['aux'][:, ~d])
+    assert (cs.info['steps'][d] == 0).all() and torch.equal(cs.info['steps'][~d], before['steps'][~d])
+    for k in ('reward', 'done', 'truncation', 'rng', 'metrics'):
+        assert torch.equal(cs.buf[k], before[k]), k
+
+
+@pytest.mark.parametrize('kind', KINDS)
+def test_pack_unpack_roundtrip_and_split_keys(kind):
+    n = 96
+    env = _make(kind, n)
+    cs = env.reset(P.keys_for(n, seed=9))
+    q = cs.qp
+    qp2, aux2 = env._pack(q)
+    assert torch.equal(qp2, cs.buf['qp'])
+    if aux2 is not None:
+        assert torch.equal(aux2, cs.buf['aux'])
+    ks = env.split_keys((0, 1234), n + 1)
+    assert (P.rng_bits(ks) == tf.split(tf.prng_key(1234), n + 1)).all()
+    part = env.split_keys((0, 1234), n + 1, first=17, count=20)
+    assert (P.rng_bits(part) == tf.split(tf.prng_key(1234), n + 1)[17:37]).all()
+
+
+def test_shard_equivalence_and_invariants():
+    """Envs never communicate: a run over N envs equals the concatenation of its shards bit for bit; at a
+    BASELINE-sized batch the state keeps its invariants (unit quaternions, finite values, 0/1 flags)."""
+    n, T = 1 << 16, 8
+    keys = torch.as_tensor(P.keys_for(n, seed=11).view(np.int32))
+    g = torch.Generator(device='cuda').manual_seed(0)
+    acts = torch.rand((T, n, 8), device='cuda', generator=g) * 2 - 1
+    full = _make('ant_heavenhell', n)
+    s = full.reset(keys)
+    for t in range(T):
+        s = full.step(s, acts[t])
+    halves = []
+    for lo, hi in ((0, n // 2), (n // 2, n)):
+        e = _make('ant_heavenhell', hi - lo)
+        h = e.reset(keys[lo:hi])
+        for t in range(T):
+            h = e.step(h, acts[t, lo:hi].contiguous())
+        halves.append(h)
+    for name in ('qp', 'aux'):
+        assert torch.equal(s.buf[name], torch.cat([h.buf[name] for h in halves], dim=1)), name
+    for name in ('obs', 'reward', 'done', 'steps', 'rng'):
+        assert torch.equal(s.buf[name], torch.cat([h.buf[name] for h in halves], dim=0)), name
+    q = s.qp
+    assert torch.isfinite(s.obs).all() and torch.isfinite(q.pos).all()
+    assert (q.rot[:, :9].norm(dim=-1) - 1).abs().max() < 1e-5
+    assert ((s.done == 0) | (s.done == 1)).all()
+    assert torch.equal(q.rot[:, 9:, 0], torch.ones_like(q.rot[:, 9:, 0]))  # frozen bodies untouched
+
+
+def test_errors_are_loud():
+    from po_brax_b200 import envs
+    with pytest.raises(ValueError):
+        envs.create('ant', batch_size=0)
+    with pytest.raises(KeyError):
+        envs.create('humanoid', batch_size=4)
+    env = envs.create('ant_tag', batch_size=4)
+    with pytest.raises(ValueError):
+        env.reset(np.zeros((3, 2), np.uint32))
+    s = env.reset(P.keys_for(4))
+    with pytest.raises(ValueError):
+        env.step(s, torch.zeros((4, 7), device='cuda'))
+    with pytest.raises(RuntimeError):
+        envs.create('ant_gather', batch_size=4, n_apples=20)

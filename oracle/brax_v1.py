@@ -207,6 +207,8 @@ class System:
                     boxes.append(np.concatenate([cpos - hs, cpos + hs]))
         self.boxes = np.array(boxes, dt).reshape(-1, 6) if walls else np.zeros((0, 6), dt)
         self.defaults = cfg.get('defaults', [])
+        self.track_margin = False   # test aid, see _note_margin
+        self.margin = None
 
     # ------------------------------------------------------------------ default_angle / default_qp
     def default_angle(self):
@@ -318,6 +320,9 @@ class System:
         t = act * self.a_strength  # brax: where(limits) then *= strength; same value
         out = (psi[:, aj] < lo[aj]) | (psi[:, aj] > hi[aj])
         t = np.where(out, zero, t).astype(self.dtype)
+        if self.track_margin:  # the actuator switches off discontinuously at the joint limits
+            m = np.minimum(np.abs(psi - lo), np.abs(psi - hi)).astype(np.float64).min(axis=-1) * 100.0
+            self.margin = m if self.margin is None else np.minimum(self.margin, m)
         a_tau = -(axis_p[:, aj] * t[..., None])
         a_dang_p = self.inv_inertia[P[aj]] * a_tau
         a_dang_c = self.inv_inertia[C[aj]] * (-a_tau)
@@ -360,9 +365,25 @@ class System:
         dpd_ang = inv_i * cross(rel, Jdv)
         apply_n = np.where((pen > zero) & (nv < zero) & (J > zero), one, zero)
         apply_d = apply_n * np.where(nd > self.dtype(0.01), one, zero)
+        if self.track_margin:
+            self._note_margin(pen, nv, J, nd)
         dvel = dpn_vel * apply_n[..., None] + dpd_vel * apply_d[..., None]
         dang = dpn_ang * apply_n[..., None] + dpd_ang * apply_d[..., None]
         return dvel.astype(self.dtype), dang.astype(self.dtype)
+
+    def _note_margin(self, pen, nv, J, nd):
+        """Test aid: distance of each contact from its nearest discontinuous branch (pen > 0, nv < 0, J > 0,
+        |v_d| > 0.01; the actuator cut-off at the joint limits is noted in _joints_and_actuators). An env whose margin is ~1 ulp may legitimately take the other branch in a different
+        float32 evaluation order (the reference's XLA program included); parity tests skip those envs."""
+        big = np.float64(1e9)
+        pen, nv, J, nd = (np.asarray(x, np.float64) for x in (pen, nv, J, nd))
+        m = np.abs(pen) * 100.0                                    # touching / not touching (length -> velocity scale)
+        live = pen > 0
+        m = np.minimum(m, np.where(live, np.abs(nv), big))         # approaching / separating
+        m = np.minimum(m, np.where(live & (nv < 0), np.abs(J), big))
+        m = np.minimum(m, np.where(live & (nv < 0) & (J > 0), np.abs(nd - 0.01), big))
+        m = m.min(axis=-1)
+        self.margin = m if self.margin is None else np.minimum(self.margin, m)
 
     def _group_reduce(self, N, body, dvel, dang):
         """Collider.apply tail: per body, sum contacts and divide by (1e-8 + #contacts with any(dvel != 0))."""

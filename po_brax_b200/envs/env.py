@@ -227,6 +227,10 @@ class Env:
         if kw.pop('walls', True) is False:  # test hook: drop the Arena colliders
             p.num_walls = 0
         kw.pop('legacy_spring', None)
+        if 'sys_dt' in kw:        # test hooks: brax config dt / substeps (sys.config.dt, sys.config.substeps)
+            p.dt = float(kw.pop('sys_dt'))
+        if 'sys_substeps' in kw:
+            p.substeps = int(kw.pop('sys_substeps'))
         if kw:
             raise TypeError(f'{name}: unexpected constructor arguments {sorted(kw)}')
 

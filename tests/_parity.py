@@ -4,6 +4,8 @@ Tolerances (stated here once, used by every parity test):
   * integers / RNG bits / done flags / item indices: bit-exact.
   * pos, rot, joint angles (teacher-forced, one env step from identical states): |d| <= 1e-6 + 2e-6*|x|
     -- SURVEY App. C gate; the float32 oracle itself is 8e-7 (pos) / 4e-7 (rot) away from its float64 twin.
+  * envs where a contact decision of the reference algorithm is rounding-ambiguous in this step (reported by the
+    oracle itself, oracle/brax_v1.py:_note_margin) are excluded from the tight gates and held to a loose bound.
   * vel, ang, joint velocities, contact impulses: |d| <= 3e-4 -- the stiff joint springs (k = 18000, h = 5 ms)
     amplify float32 rounding of positions: the float32 oracle is up to 1.1e-4 away from the float64 oracle
     after one step (measured over 60 steps x 256 envs), so 3e-4 is ~3x the reference arithmetic's own noise.
@@ -17,6 +19,10 @@ from oracle import threefry as tf
 
 POS_TOL = (1e-6, 2e-6)
 VEL_ATOL = 3e-4
+# An env counts as rounding-ambiguous when a contact is within this margin of a discontinuous branch
+# (margins are in velocity units; penetration margins are scaled x100, see below).
+BRANCH_MARGIN = 5e-4
+LOOSE_POS, LOOSE_VEL = 2e-2, 3.0   # ambiguous envs: one contact impulse / one actuator cut-off (350*h = 1.75 rad/s) apart
 
 
 def keys_for(n, seed=0):
@@ -48,10 +54,18 @@ def close_pos(a, b):
     return np.abs(a - b) <= POS_TOL[0] + POS_TOL[1] * np.abs(b)
 
 
-def assert_qp_close(got, want, what='', vel_atol=VEL_ATOL):
+def assert_qp_close(got, want, what='', vel_atol=VEL_ATOL, rows=None, loose=False, pos_scale=1.0):
     for name, tight in (('pos', True), ('rot', True), ('vel', False), ('ang', False)):
         g, w = t2n(getattr(got, name)), getattr(want, name)
-        ok = close_pos(g, w) if tight else (np.abs(g - w) <= vel_atol)
+        if rows is not None:
+            g, w = g[rows], w[rows]
+        if g.size == 0:
+            continue
+        if loose:
+            ok = np.abs(g - w) <= (LOOSE_POS if tight else LOOSE_VEL)
+        else:
+            ok = (np.abs(g - w) <= pos_scale * (POS_TOL[0] + POS_TOL[1] * np.abs(w))) if tight else \
+                 (np.abs(g - w) <= vel_atol)
         assert ok.all(), f'{what} qp.{name}: max |d| = {np.abs(g - w).max():.3e} at {np.argwhere(~ok)[:4].tolist()}'
 
 

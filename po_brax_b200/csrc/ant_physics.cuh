@@ -143,29 +143,32 @@ __device__ __forceinline__ float seg_box_t(V3 a, V3 d, V3 lo, V3 hi) {
   return den > 0.0f ? tl - gl * (tr - tl) / den : tl;
 }
 
-// Lower bound of the xy-distance from (x, y) to the nearest wall (conservative; 0 outside the table).
-__device__ __forceinline__ float sdf_at(const DevConst& C, float x, float y) {
+// Candidate walls of a body centred at (x, y): bit w set <=> wall w is within the largest capsule reach of the
+// table cell (exact rectangle-rectangle distance, so culling stays exact); every wall outside the table.
+__device__ __forceinline__ unsigned wall_mask_at(const DevConst& C, float x, float y) {
   const float fx = (x - C.sdf_x0) * C.sdf_inv_cell, fy = (y - C.sdf_y0) * C.sdf_inv_cell;
   const int ix = min(max((int)fx, 0), C.sdf_nx - 1);
   const int iy = min(max((int)fy, 0), C.sdf_ny - 1);
-  return __ldg(C.sdf + iy * C.sdf_nx + ix);
+  return __ldg(C.wall_mask + iy * C.sdf_nx + ix);
 }
 
-// Capsule (segment p + ea .. p + eb, radius r) vs every Arena box: one contact per box at the closest
-// box point; per body the contacts are summed and divided by (1e-8 + #contacts with a non-zero dv).
-// Exact culling: a pair further apart than r contributes exactly zero (pen <= 0).
-__device__ __noinline__ void wall_contacts(const Body& b, V3 ea, V3 eb, float r, float reach, float inv_m,
-                                           const DevConst& C, V3& dv, V3& dw) {
+// Capsule (segment p + e .. p - e, radius r) vs the candidate Arena boxes in `mask`: one contact per box at
+// the closest box point; per body the contacts are summed and divided by (1e-8 + #contacts with a non-zero
+// dv). Exact culling: a pair further apart than r contributes exactly zero (pen <= 0).
+__device__ __forceinline__ void wall_contacts(const Body& b, V3 e, float r, float reach, float inv_m, unsigned mask,
+                                              const DevConst& C, V3& dv, V3& dw) {
   V3 sv = mk(0.f, 0.f, 0.f), sw = mk(0.f, 0.f, 0.f);
   float cnt = 0.0f;
   const float reach2 = reach * reach;
-  for (int w = 0; w < C.n_walls; ++w) {
+  while (mask) {
+    const int w = __ffs(mask) - 1;
+    mask &= mask - 1;
     const V3 lo = mk(C.wall_lo[w][0], C.wall_lo[w][1], C.wall_lo[w][2]);
     const V3 hi = mk(C.wall_hi[w][0], C.wall_hi[w][1], C.wall_hi[w][2]);
     const V3 cd = b.p - clamp3(b.p, lo, hi);
     if (dot(cd, cd) > reach2) continue;
-    const V3 a = b.p + ea;
-    const V3 d = (b.p + eb) - a;
+    const V3 a = b.p + e;
+    const V3 d = (b.p - e) - a;
     const float t = seg_box_t(a, d, lo, hi);
     const V3 sp = a + t * d;
     const V3 bp = clamp3(sp, lo, hi);
@@ -220,14 +223,26 @@ __device__ __forceinline__ void contacts(const Rig& r, const LegK& k, const DevC
   ground_contact(r.T, mk(0.f, 0.f, 0.f), C.r_torso, C.inv_m_torso, C, ct.Tv, ct.Tw);
   ground_contact(r.B, C.s_foot * dB, C.r_leg, C.inv_m_leg, C, ct.Bv, ct.Bw);
   if (WALLS) {
-    const float reach_t = C.r_torso + 1e-4f, reach_a = C.seg_aux + C.r_leg + 1e-4f,
-                reach_b = C.seg_foot + C.r_leg + 1e-4f;
-    if (sdf_at(C, r.T.p.x, r.T.p.y) <= reach_t)
-      wall_contacts(r.T, mk(0.f, 0.f, 0.f), mk(0.f, 0.f, 0.f), C.r_torso, reach_t, C.inv_m_torso, C, ct.Tv, ct.Tw);
-    if (sdf_at(C, r.A.p.x, r.A.p.y) <= reach_a)
-      wall_contacts(r.A, C.s_aux * dA, -C.s_aux * dA, C.r_leg, reach_a, C.inv_m_leg, C, ct.Av, ct.Aw);
-    if (sdf_at(C, r.B.p.x, r.B.p.y) <= reach_b)
-      wall_contacts(r.B, C.s_foot * dB, -C.s_foot * dB, C.r_leg, reach_b, C.inv_m_leg, C, ct.Bv, ct.Bw);
+    const unsigned mT = wall_mask_at(C, r.T.p.x, r.T.p.y), mA = wall_mask_at(C, r.A.p.x, r.A.p.y),
+                   mB = wall_mask_at(C, r.B.p.x, r.B.p.y);
+    if ((mT | mA | mB) != 0u) {
+      // one copy of the narrow phase: loop over the lane's bodies, selecting the operands
+#pragma unroll 1
+      for (int i = 0; i < 3; ++i) {
+        const unsigned m = i == 0 ? mT : (i == 1 ? mA : mB);
+        if (m == 0u) continue;
+        const Body X = i == 0 ? r.T : (i == 1 ? r.A : r.B);
+        const float se = i == 0 ? 0.0f : (i == 1 ? C.s_aux : C.s_foot);
+        const V3 d = i == 1 ? dA : dB;
+        const float rad = i == 0 ? C.r_torso : C.r_leg;
+        const float reach = (i == 0 ? C.r_torso : (i == 1 ? C.seg_aux + C.r_leg : C.seg_foot + C.r_leg)) + 1e-4f;
+        V3 dv = mk(0.f, 0.f, 0.f), dw = mk(0.f, 0.f, 0.f);
+        wall_contacts(X, se * d, rad, reach, i == 0 ? C.inv_m_torso : C.inv_m_leg, m, C, dv, dw);
+        if (i == 0) { ct.Tv += dv; ct.Tw += dw; }
+        else if (i == 1) { ct.Av += dv; ct.Aw += dw; }
+        else { ct.Bv += dv; ct.Bw += dw; }
+      }
+    }
   }
 }
 

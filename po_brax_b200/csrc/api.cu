@@ -26,7 +26,7 @@ cudaError_t launch_fma_probe(float* out, int blocks, int iters, cudaStream_t st)
 struct Handle {
   DevConst C;
   int device;
-  float* sdf = nullptr;
+  uint8_t* sdf = nullptr;  // wall candidate mask table
   float2* grid = nullptr;
 };
 }  // namespace pobrax
@@ -209,7 +209,7 @@ static std::vector<float2> gather_grid(const PobraxParams* p) {
   return g;
 }
 
-static int build_dev_const(const PobraxParams* p, DevConst* Cp, std::vector<float>* sdf, std::vector<float2>* grid) {
+static int build_dev_const(const PobraxParams* p, DevConst* Cp, std::vector<uint8_t>* sdf, std::vector<float2>* grid) {
   DevConst& C = *Cp;
   std::memset(&C, 0, sizeof(C));
   PobraxLayout L;
@@ -301,18 +301,23 @@ static int build_dev_const(const PobraxParams* p, DevConst* Cp, std::vector<floa
     x0 -= margin; y0 -= margin; x1 += margin; y1 += margin;
     const int nx = (int)std::ceil((x1 - x0) / cell), ny = (int)std::ceil((y1 - y0) / cell);
     if (nx <= 2 || ny <= 2 || (long long)nx * ny > (1 << 22)) return fail("wall extent unsupported (distance field too large)");
-    sdf->assign((size_t)nx * ny, 0.0f);
-    const double half_diag = cell * std::sqrt(0.5) * 1.0001 + 1e-4;
+    // Bit w of a cell: some point of the cell is within `reach` (largest capsule bounding radius, plus slack
+    // for the float cell lookup) of wall w in the xy-plane. Border cells (and everything outside the table,
+    // which clamps onto them) list every wall.
+    const uint8_t all = (uint8_t)((1u << C.n_walls) - 1u);
+    sdf->assign((size_t)nx * ny, all);
+    const double reach = std::fmax(C.r_torso, std::fmax(C.seg_aux, C.seg_foot) + C.r_leg) + 1e-3;
     for (int iy = 1; iy < ny - 1; ++iy)
       for (int ix = 1; ix < nx - 1; ++ix) {
-        const double cx = x0 + (ix + 0.5) * cell, cy = y0 + (iy + 0.5) * cell;
-        double best = 1e30;
+        const double cx0 = x0 + ix * cell - 1e-4, cx1 = x0 + (ix + 1) * cell + 1e-4;
+        const double cy0 = y0 + iy * cell - 1e-4, cy1 = y0 + (iy + 1) * cell + 1e-4;
+        uint8_t m = 0;
         for (int w = 0; w < C.n_walls; ++w) {
-          const double dx = std::fmax(std::fmax(C.wall_lo[w][0] - cx, 0.0), cx - C.wall_hi[w][0]);
-          const double dy = std::fmax(std::fmax(C.wall_lo[w][1] - cy, 0.0), cy - C.wall_hi[w][1]);
-          best = std::fmin(best, std::sqrt(dx * dx + dy * dy));
+          const double dx = std::fmax(std::fmax(C.wall_lo[w][0] - cx1, 0.0), cx0 - C.wall_hi[w][0]);
+          const double dy = std::fmax(std::fmax(C.wall_lo[w][1] - cy1, 0.0), cy0 - C.wall_hi[w][1]);
+          if (std::sqrt(dx * dx + dy * dy) <= reach) m |= (uint8_t)(1u << w);
         }
-        (*sdf)[(size_t)iy * nx + ix] = (float)std::fmax(0.0, best - half_diag);
+        (*sdf)[(size_t)iy * nx + ix] = m;
       }
     C.sdf_x0 = (float)x0; C.sdf_y0 = (float)y0; C.sdf_inv_cell = (float)(1.0 / cell);
     C.sdf_nx = nx; C.sdf_ny = ny;
@@ -351,7 +356,7 @@ extern "C" int pobrax_create(const PobraxParams* p, int device, void** handle) {
   if (!p || !handle) return fail("pobrax_create: null argument");
   *handle = nullptr;
   DevConst C;
-  std::vector<float> sdf;
+  std::vector<uint8_t> sdf;
   std::vector<float2> grid;
   if (int rc = build_dev_const(p, &C, &sdf, &grid)) return rc;
   int count = 0;
@@ -367,14 +372,14 @@ extern "C" int pobrax_create(const PobraxParams* p, int device, void** handle) {
   Handle* h = new Handle();
   h->device = device;
   if (!sdf.empty()) {
-    if ((e = cudaMalloc(&h->sdf, sdf.size() * sizeof(float))) != cudaSuccess) { delete h; cudaSetDevice(prev); return fail_cuda("cudaMalloc(sdf)", e); }
-    cudaMemcpy(h->sdf, sdf.data(), sdf.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if ((e = cudaMalloc(&h->sdf, sdf.size())) != cudaSuccess) { delete h; cudaSetDevice(prev); return fail_cuda("cudaMalloc(sdf)", e); }
+    cudaMemcpy(h->sdf, sdf.data(), sdf.size(), cudaMemcpyHostToDevice);
   }
   if (!grid.empty()) {
     if ((e = cudaMalloc(&h->grid, grid.size() * sizeof(float2))) != cudaSuccess) { cudaFree(h->sdf); delete h; cudaSetDevice(prev); return fail_cuda("cudaMalloc(grid)", e); }
     cudaMemcpy(h->grid, grid.data(), grid.size() * sizeof(float2), cudaMemcpyHostToDevice);
   }
-  C.sdf = h->sdf;
+  C.wall_mask = h->sdf;
   h->C = C;
   cudaSetDevice(prev);
   *handle = h;

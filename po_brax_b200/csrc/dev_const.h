@@ -46,9 +46,9 @@ struct DevConst {
   float hip_lo, hip_hi;                      // hip: axis e_z, ref -e_x, limits uniform over legs
   float ank_lo[4], ank_hi[4];
   float hip_default, ank_default[4];         // default_angle(): limit midpoints
-  // walls: axis-aligned boxes in world coordinates + a conservative distance field for exact culling
+  // walls: axis-aligned boxes in world coordinates + a per-cell candidate mask for exact culling
   float wall_lo[kMaxWalls][3], wall_hi[kMaxWalls][3];
-  const float* sdf;                          // [sdf_ny][sdf_nx] lower bound of xy-distance to the nearest wall
+  const uint8_t* wall_mask;                  // [sdf_ny][sdf_nx] candidate-wall bit mask of each xy cell (exact culling)
   float sdf_x0, sdf_y0, sdf_inv_cell;
   int32_t sdf_nx, sdf_ny;
   // task

@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""Minimal driver for ncu: reset + a few fused steps of one env family (no timing, no extras).
+    python tools/profile_step.py --env ant_heavenhell --envs 1048576 --steps 6 [--spread 60]
+--spread K: run K un-profiled... no: steps before the profiled window so envs are spread over episode phases."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from po_brax_b200 import envs  # noqa: E402
+from po_brax_b200.parallel import shard_keys  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--env', default='ant_heavenhell')
+ap.add_argument('--envs', type=int, default=1 << 20)
+ap.add_argument('--steps', type=int, default=6)
+a = ap.parse_args()
+env = envs.create(a.env, batch_size=a.envs, episode_length=1000, auto_reset=True, eval_metrics=True)
+state = env.reset(shard_keys(env, 0, a.envs, 0, 1))
+g = torch.Generator(device='cuda').manual_seed(1234)
+acts = torch.rand((4, a.envs, 8), device='cuda', generator=g) * 2 - 1
+for i in range(a.steps):
+    state = env.step(state, acts[i % 4])
+torch.cuda.synchronize()
+print('ok', float(state.reward.sum()))

@@ -48,22 +48,37 @@ __device__ __forceinline__ void kinetic(Body& b, float h) {
   b.qw = w * r; b.qx = x * r; b.qy = y * r; b.qz = z * r;
 }
 
-// Revolute.apply + Torque.apply for one joint. rp/rc: world-frame lever arms (rotated offsets).
-// Outputs F (force on the child; -F on the parent) and tau (torque on the parent; -tau on the child,
-// actuator torque included). SURVEY App. A.3 "joints" + "actuators".
-__device__ __forceinline__ void joint_force(const Body& P, const Body& Cb, V3 rp, V3 rc, V3 axis_p, V3 axis_c,
-                                            V3 ref_p, V3 ref_c, float lo, float hi, float act,
-                                            const DevConst& C, V3& F, V3& tau) {
-  const V3 dpos = (P.p - Cb.p) + (rp - rc);
-  const V3 dvel = (P.v - Cb.v) + (cross(P.w, rp) - cross(Cb.w, rc));
-  F = C.k_joint * dpos + C.sd_joint * dvel;
-  const float psi = atan2f(dot(cross(ref_p, ref_c), axis_p), dot(ref_p, ref_c));
+// atan2 for the joint-limit logic of the substep loop: octant reduction + degree-7 minimax polynomial in t^2
+// (max abs error 1.3e-7 rad incl. float32 rounding, i.e. the same 1-2 ulp class as atan2f, at ~40% of its
+// instruction count; no special-case handling: the arguments are products of unit vectors, never both zero).
+__device__ __forceinline__ float atan2_fast(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float t = __fdividef(mn, mx);
+  const float s = t * t;
+  float p = -0.004054381512105465f;
+  p = fmaf(p, s, 0.021862255409359932f);
+  p = fmaf(p, s, -0.055911269038915634f);
+  p = fmaf(p, s, 0.09642115980386734f);
+  p = fmaf(p, s, -0.13908596336841583f);
+  p = fmaf(p, s, 0.1994655877351761f);
+  p = fmaf(p, s, -0.33329859375953674f);
+  p = fmaf(p, s, 0.9999993443489075f);
+  float r = p * t;
+  r = ay > ax ? 1.57079632679489662f - r : r;
+  r = x < 0.0f ? 3.14159265358979324f - r : r;
+  return copysignf(r, y);
+}
+
+// Joint limit + actuator scalar of one joint: returns h*(limitStrength*dang + t) where dang is the limit
+// violation and t the actuator torque (zeroed outside the limits). SURVEY App. A.3 "joints"/"actuators".
+__device__ __forceinline__ float limit_and_actuator(float sin_psi, float cos_psi, float lo, float hi, float act,
+                                                    const DevConst& C) {
+  const float psi = atan2_fast(sin_psi, cos_psi);
   const bool below = psi < lo, above = psi > hi;
   const float dang = above ? hi - psi : (below ? lo - psi : 0.0f);
-  const float t = (below || above) ? 0.0f : act * C.act_strength;
-  // tau = k (axis_p x axis_c) - limitStrength*axis_p*dang - angularDamping*(w_p - w_c) - t*axis_p
-  const float s = fmaf(C.ls_joint, dang, t);
-  tau = C.k_joint * cross(axis_p, axis_c) - s * axis_p - C.ad_joint * (P.w - Cb.w);
+  const float t = (below || above) ? 0.0f : act * C.h_act;
+  return fmaf(C.h_ls, dang, t);
 }
 
 // Joint angle and velocity for the observation (Revolute.angle_vel): psi as above, vel = (w_p - w_c).axis_p
@@ -73,48 +88,58 @@ __device__ __forceinline__ void joint_angle_vel(const Body& P, const Body& Cb, V
   vel = dot(P.w - Cb.w, axis_p);
 }
 
+struct Imp { V3 dv, dw; float hit; };  // one contact's (dvel, dang) and whether it is non-zero
+
 // OneWayCollider contact impulse on a unit-inertia body, general normal.
-// rel = contact point - body pos, v = contact point velocity. Adds nothing when pen <= 0.
-__device__ __forceinline__ bool impulse(V3 rel, V3 v, V3 n, float pen, float inv_m, const DevConst& C, V3& dv,
-                                        V3& dw) {
-  const float bv = C.baumgarte * pen;
+// rel = contact point - body pos, v = contact point velocity. Zero when pen <= 0.
+__device__ __forceinline__ Imp impulse(V3 rel, V3 v, V3 n, float pen, float inv_m, float baumgarte, float friction,
+                                       float elasticity) {
+  Imp o;
+  o.dv = o.dw = mk(0.f, 0.f, 0.f);
+  o.hit = 0.0f;
   const float nv = dot(n, v);
   const V3 t1 = cross(rel, n);
-  const float ang = dot(n, cross(t1, rel));
-  const float denom = inv_m + ang;
-  const float J = (bv - (1.0f + C.elasticity) * nv) / denom;
-  const bool apply_n = (pen > 0.0f) && (nv < 0.0f) && (J > 0.0f);
-  dv = mk(0.f, 0.f, 0.f);
-  dw = mk(0.f, 0.f, 0.f);
-  if (!apply_n) return false;
+  const float rden = __fdividef(1.0f, inv_m + dot(n, cross(t1, rel)));
+  const float J = (baumgarte * pen - (1.0f + elasticity) * nv) * rden;
+  if (!((pen > 0.0f) && (nv < 0.0f) && (J > 0.0f))) return o;
   const V3 Jn = J * n;
-  dv = inv_m * Jn;
-  dw = cross(rel, Jn);
+  o.dv = inv_m * Jn;
+  o.dw = cross(rel, Jn);
   const V3 vd = v - nv * n;
   const float nd = sqrtf(dot(vd, vd));
   if (nd > 0.01f) {
-    const float Jd = fminf(nd / denom, C.friction * J);
-    const V3 Jdv = (-Jd / (1e-6f + nd)) * vd;
-    dv += inv_m * Jdv;
-    dw += cross(rel, Jdv);
+    const float Jd = fminf(nd * rden, friction * J);
+    const V3 Jdv = __fdividef(-Jd, 1e-6f + nd) * vd;
+    o.dv += inv_m * Jdv;
+    o.dw += cross(rel, Jdv);
   }
-  return (dv.x != 0.0f) || (dv.y != 0.0f) || (dv.z != 0.0f);
+  o.hit = ((o.dv.x != 0.0f) || (o.dv.y != 0.0f) || (o.dv.z != 0.0f)) ? 1.0f : 0.0f;
+  return o;
 }
 
-// Capsule-end vs ground plane (normal +z through the origin), SURVEY App. A.3 "colliders".
-// e = world-frame offset of the capsule end from the body position.
-__device__ __forceinline__ void ground_contact(const Body& b, V3 e, float r, float inv_m, const DevConst& C,
-                                               V3& dv, V3& dw) {
-  const float cz = (b.p.z + e.z) - r;
-  const float pen = -cz;
-  if (pen > 0.0f) {
-    const V3 rel = mk(e.x, e.y, e.z - r);
-    const V3 v = b.v + cross(b.w, rel);
-    V3 a, c;
-    impulse(rel, v, mk(0.f, 0.f, 1.f), pen, inv_m, C, a, c);
-    dv += a;
-    dw += c;
+// Capsule-end vs ground plane (normal +z through the origin) for the foot, the one contact that is live on
+// most substeps: `impulse` written out for n = e_z. e = world-frame offset of the capsule end from the body.
+__device__ __forceinline__ bool foot_ground(const Body& b, V3 e, float r, float inv_m, const DevConst& C, V3& dv,
+                                            V3& dw) {
+  const float pen = r - (b.p.z + e.z);
+  if (!(pen > 0.0f)) return false;
+  const float rx = e.x, ry = e.y, rz = e.z - r;
+  const float vx = b.v.x + (b.w.y * rz - b.w.z * ry);
+  const float vy = b.v.y + (b.w.z * rx - b.w.x * rz);
+  const float nv = b.v.z + (b.w.x * ry - b.w.y * rx);
+  const float rden = __fdividef(1.0f, inv_m + (rx * rx + ry * ry));
+  const float J = (C.baumgarte * pen - (1.0f + C.elasticity) * nv) * rden;
+  if (!((nv < 0.0f) && (J > 0.0f))) return false;
+  dv = mk(0.f, 0.f, inv_m * J);
+  dw = mk(ry * J, -rx * J, 0.f);
+  const float nd = sqrtf(vx * vx + vy * vy);
+  if (nd > 0.01f) {
+    const float c = __fdividef(-fminf(nd * rden, C.friction * J), 1e-6f + nd);
+    const float jx = c * vx, jy = c * vy;
+    dv.x = inv_m * jx; dv.y = inv_m * jy;
+    dw.x -= rz * jy; dw.y += rz * jx; dw.z = rx * jy - ry * jx;
   }
+  return true;
 }
 
 __device__ __forceinline__ V3 clamp3(V3 p, V3 lo, V3 hi) {
@@ -143,6 +168,35 @@ __device__ __forceinline__ float seg_box_t(V3 a, V3 d, V3 lo, V3 hi) {
   return den > 0.0f ? tl - gl * (tr - tl) / den : tl;
 }
 
+// The rare contacts, out of line so the substep loop stays small (I-cache) and lean (registers):
+//  plane = 0: capsule (segment p + e .. p - e, radius rad) vs the axis-aligned Arena box [lo, hi]: one contact at
+//             the closest box point, normal (seg_pt - box_pt)/(1e-6 + d), penetration rad - d;
+//  plane = 1: sphere (e = 0) vs the ground plane z = 0 (the torso's capsule_plane candidate).
+__device__ __noinline__ Imp contact_general(V3 p, V3 e, V3 v, V3 w, float rad, float inv_m, V3 lo, V3 hi, int plane,
+                                            float baumgarte, float friction, float elasticity) {
+  if (plane) {
+    const V3 rel = mk(0.f, 0.f, -rad);
+    return impulse(rel, v + cross(w, rel), mk(0.f, 0.f, 1.f), rad - p.z, inv_m, baumgarte, friction, elasticity);
+  }
+  const V3 a = p + e;
+  const V3 d = (p - e) - a;
+  const float t = seg_box_t(a, d, lo, hi);
+  const V3 sp = a + t * d;
+  const V3 bp = clamp3(sp, lo, hi);
+  const V3 dvec = sp - bp;
+  const float dist = sqrtf(dot(dvec, dvec));
+  const float pen = rad - dist;
+  if (!(pen > 0.0f)) {
+    Imp o;
+    o.dv = o.dw = mk(0.f, 0.f, 0.f);
+    o.hit = 0.0f;
+    return o;
+  }
+  const V3 n = (1.0f / (1e-6f + dist)) * dvec;
+  const V3 rel = bp - p;
+  return impulse(rel, v + cross(w, rel), n, pen, inv_m, baumgarte, friction, elasticity);
+}
+
 // Candidate walls of a body centred at (x, y): bit w set <=> wall w is within the largest capsule reach of the
 // table cell (exact rectangle-rectangle distance, so culling stays exact); every wall outside the table.
 __device__ __forceinline__ unsigned wall_mask_at(const DevConst& C, float x, float y) {
@@ -150,44 +204,6 @@ __device__ __forceinline__ unsigned wall_mask_at(const DevConst& C, float x, flo
   const int ix = min(max((int)fx, 0), C.sdf_nx - 1);
   const int iy = min(max((int)fy, 0), C.sdf_ny - 1);
   return __ldg(C.wall_mask + iy * C.sdf_nx + ix);
-}
-
-// Capsule (segment p + e .. p - e, radius r) vs the candidate Arena boxes in `mask`: one contact per box at
-// the closest box point; per body the contacts are summed and divided by (1e-8 + #contacts with a non-zero
-// dv). Exact culling: a pair further apart than r contributes exactly zero (pen <= 0).
-__device__ __forceinline__ void wall_contacts(const Body& b, V3 e, float r, float reach, float inv_m, unsigned mask,
-                                              const DevConst& C, V3& dv, V3& dw) {
-  V3 sv = mk(0.f, 0.f, 0.f), sw = mk(0.f, 0.f, 0.f);
-  float cnt = 0.0f;
-  const float reach2 = reach * reach;
-  while (mask) {
-    const int w = __ffs(mask) - 1;
-    mask &= mask - 1;
-    const V3 lo = mk(C.wall_lo[w][0], C.wall_lo[w][1], C.wall_lo[w][2]);
-    const V3 hi = mk(C.wall_hi[w][0], C.wall_hi[w][1], C.wall_hi[w][2]);
-    const V3 cd = b.p - clamp3(b.p, lo, hi);
-    if (dot(cd, cd) > reach2) continue;
-    const V3 a = b.p + e;
-    const V3 d = (b.p - e) - a;
-    const float t = seg_box_t(a, d, lo, hi);
-    const V3 sp = a + t * d;
-    const V3 bp = clamp3(sp, lo, hi);
-    const V3 dvec = sp - bp;
-    const float dist = sqrtf(dot(dvec, dvec));
-    const float pen = r - dist;
-    if (pen > 0.0f) {
-      const V3 n = (1.0f / (1e-6f + dist)) * dvec;
-      const V3 rel = bp - b.p;
-      const V3 v = b.v + cross(b.w, rel);
-      V3 a1, c1;
-      if (impulse(rel, v, n, pen, inv_m, C, a1, c1)) cnt += 1.0f;
-      sv += a1;
-      sw += c1;
-    }
-  }
-  const float inv = 1.0f / (1e-8f + cnt);
-  dv += inv * sv;
-  dw += inv * sw;
 }
 
 // Per-lane constants of leg l.
@@ -206,7 +222,14 @@ __device__ __forceinline__ LegK leg_consts(const DevConst& C, int leg) {
 }
 
 struct Rig { Body T, A, B; };                 // one lane: torso replica + its leg
-struct Contact { V3 Tv, Tw, Av, Aw, Bv, Bw; };  // contact impulses (dvel, dang) of the lane's three bodies
+// Info.contact accumulators of the lane: the foot's (hot) live in registers; the torso's and the Aux body's
+// (torso-ground and wall contacts only) accumulate straight into the env's staged observation row in shared
+// memory (cv / ca = the row's contact.vel / contact.ang blocks, [nb][3] each), clipped when the row is finalised.
+struct ContactAcc { V3 Bv, Bw; float* cv; float* ca; };
+
+__device__ __forceinline__ void row_add(float* base, int body, V3 a) {
+  base[3 * body] += a.x; base[3 * body + 1] += a.y; base[3 * body + 2] += a.z;
+}
 
 __device__ __forceinline__ float quad_sum(float x) {
   x += __shfl_xor_sync(kFull, x, 1);
@@ -215,84 +238,131 @@ __device__ __forceinline__ float quad_sum(float x) {
 }
 __device__ __forceinline__ V3 quad_sum(V3 a) { return mk(quad_sum(a.x), quad_sum(a.y), quad_sum(a.z)); }
 
-// Σ colliders.apply(qp) for the lane's bodies: ground (torso sphere, foot end) + Arena walls (all three).
+// Σ colliders.apply(qp) for the lane's bodies -- ground (torso sphere, foot end) + Arena walls (all three) --
+// evaluated on the state in `r`; then integrators.collision (vel += dv, ang += dw) and the Info.contact sums.
+// Every contact is evaluated on the same (pre-collision) state: a body's impulses are applied only after all
+// of that body's contacts have been evaluated. A body has at most one ground candidate, so the ground
+// group's "divide by the active count" is a no-op; the wall group divides per body.
 template <bool WALLS>
-__device__ __forceinline__ void contacts(const Rig& r, const LegK& k, const DevConst& C, V3 dA, V3 dB,
-                                         Contact& ct) {
-  ct.Tv = ct.Tw = ct.Av = ct.Aw = ct.Bv = ct.Bw = mk(0.f, 0.f, 0.f);
-  ground_contact(r.T, mk(0.f, 0.f, 0.f), C.r_torso, C.inv_m_torso, C, ct.Tv, ct.Tw);
-  ground_contact(r.B, C.s_foot * dB, C.r_leg, C.inv_m_leg, C, ct.Bv, ct.Bw);
-  if (WALLS) {
-    const unsigned mT = wall_mask_at(C, r.T.p.x, r.T.p.y), mA = wall_mask_at(C, r.A.p.x, r.A.p.y),
-                   mB = wall_mask_at(C, r.B.p.x, r.B.p.y);
-    if ((mT | mA | mB) != 0u) {
-      // one copy of the narrow phase: loop over the lane's bodies, selecting the operands
+__device__ __forceinline__ void contacts(Rig& r, const DevConst& C, V3 dA, V3 dB, unsigned masks, int leg,
+                                         ContactAcc& acc) {
+  V3 gv, gw;
+  const bool hitB = foot_ground(r.B, C.s_foot * dB, C.r_leg, C.inv_m_leg, C, gv, gw);
+  const V3 zero = mk(0.f, 0.f, 0.f);
+  Imp gT;
+  const bool hitT = C.r_torso - r.T.p.z > 0.0f;
+  if (hitT)
+    gT = contact_general(r.T.p, zero, r.T.v, r.T.w, C.r_torso, C.inv_m_torso, zero, zero, 1, C.baumgarte, C.friction,
+                         C.elasticity);
+  if (WALLS && masks != 0u) {
 #pragma unroll 1
-      for (int i = 0; i < 3; ++i) {
-        const unsigned m = i == 0 ? mT : (i == 1 ? mA : mB);
-        if (m == 0u) continue;
-        const Body X = i == 0 ? r.T : (i == 1 ? r.A : r.B);
-        const float se = i == 0 ? 0.0f : (i == 1 ? C.s_aux : C.s_foot);
-        const V3 d = i == 1 ? dA : dB;
-        const float rad = i == 0 ? C.r_torso : C.r_leg;
-        const float reach = (i == 0 ? C.r_torso : (i == 1 ? C.seg_aux + C.r_leg : C.seg_foot + C.r_leg)) + 1e-4f;
-        V3 dv = mk(0.f, 0.f, 0.f), dw = mk(0.f, 0.f, 0.f);
-        wall_contacts(X, se * d, rad, reach, i == 0 ? C.inv_m_torso : C.inv_m_leg, m, C, dv, dw);
-        if (i == 0) { ct.Tv += dv; ct.Tw += dw; }
-        else if (i == 1) { ct.Av += dv; ct.Aw += dw; }
-        else { ct.Bv += dv; ct.Bw += dw; }
+    for (int i = 0; i < 3; ++i) {  // one copy of the pair loop; operands selected per body
+      unsigned m = (masks >> (8 * i)) & 0xffu;
+      if (m == 0u) continue;
+      const V3 p = i == 0 ? r.T.p : (i == 1 ? r.A.p : r.B.p);
+      const float reach = (i == 0 ? C.r_torso : (i == 1 ? C.seg_aux + C.r_leg : C.seg_foot + C.r_leg)) + 1e-4f;
+      V3 sv = zero, sw = zero;
+      float cnt = 0.0f;
+      bool any = false;
+      while (m) {
+        const int w = __ffs(m) - 1;
+        m &= m - 1;
+        const V3 lo = mk(C.wall_lo[w][0], C.wall_lo[w][1], C.wall_lo[w][2]);
+        const V3 hi = mk(C.wall_hi[w][0], C.wall_hi[w][1], C.wall_hi[w][2]);
+        const V3 cd = p - clamp3(p, lo, hi);
+        if (dot(cd, cd) > reach * reach) continue;  // exact: further than the capsule's reach => pen <= 0
+        const V3 v = i == 0 ? r.T.v : (i == 1 ? r.A.v : r.B.v);
+        const V3 wv = i == 0 ? r.T.w : (i == 1 ? r.A.w : r.B.w);
+        const V3 e = i == 0 ? zero : (i == 1 ? C.s_aux * dA : C.s_foot * dB);
+        const Imp c = contact_general(p, e, v, wv, i == 0 ? C.r_torso : C.r_leg, i == 0 ? C.inv_m_torso : C.inv_m_leg,
+                                      lo, hi, 0, C.baumgarte, C.friction, C.elasticity);
+        sv += c.dv; sw += c.dw; cnt += c.hit;
+        any = true;
+      }
+      if (any) {
+        const float inv = 1.0f / (1e-8f + cnt);
+        const V3 dv = inv * sv, dw = inv * sw;
+        if (i == 0) {
+          r.T.v += dv; r.T.w += dw;
+          if (leg == 0) { row_add(acc.cv, 0, dv); row_add(acc.ca, 0, dw); }
+        } else if (i == 1) {
+          r.A.v += dv; r.A.w += dw;
+          row_add(acc.cv, 1 + 2 * leg, dv); row_add(acc.ca, 1 + 2 * leg, dw);
+        } else {
+          r.B.v += dv; r.B.w += dw;
+          acc.Bv += dv; acc.Bw += dw;
+        }
       }
     }
+  }
+  if (hitB) {
+    r.B.v += gv; r.B.w += gw;
+    acc.Bv += gv; acc.Bw += gw;
+  }
+  if (hitT) {
+    r.T.v += gT.dv; r.T.w += gT.dw;
+    if (leg == 0) { row_add(acc.cv, 0, gT.dv); row_add(acc.ca, 0, gT.dw); }
   }
 }
 
 // One physics substep for the lane's three bodies. act_h / act_a: hip / ankle actions.
+// All impulses carry the factor h (C.h_k = h*stiffness, ...), so `potential` is a plain add.
 template <bool WALLS>
-__device__ __forceinline__ void substep(Rig& r, const LegK& k, float act_h, float act_a, const DevConst& C,
-                                        Contact& acc) {
-  const float h = C.h;
-  kinetic(r.T, h);
-  kinetic(r.A, h);
-  kinetic(r.B, h);
+__device__ __forceinline__ void substep(Rig& r, const LegK& k, float act_h, float act_a, const DevConst& C, int leg,
+                                        ContactAcc& acc) {
+  kinetic(r.T, C.h);
+  kinetic(r.A, C.h);
+  kinetic(r.B, C.h);
+  // positions are final for this substep: fetch the candidate-wall masks now, use them after the joint math
+  unsigned masks = 0u;
+  if (WALLS)
+    masks = wall_mask_at(C, r.T.p.x, r.T.p.y) | (wall_mask_at(C, r.A.p.x, r.A.p.y) << 8) |
+            (wall_mask_at(C, r.B.p.x, r.B.p.y) << 16);
   const Cols cT = rot_cols(r.T), cA = rot_cols(r.A), cB = rot_cols(r.B);
-  const V3 dT = k.ux * cT.c0 + k.uy * cT.c1;  // R_T u
+  const V3 dT = k.ux * cT.c0 + k.uy * cT.c1;  // R_T u: every lever arm of the leg is a scalar times dT / dA / dB
   const V3 dA = k.ux * cA.c0 + k.uy * cA.c1;
   const V3 dB = k.ux * cB.c0 + k.uy * cB.c1;
-  // hip: Torso -> Aux. axis e_z, ref -e_x (the two minus signs cancel inside atan2)
-  V3 Fh, th;
-  joint_force(r.T, r.A, C.s_hip_p * dT, C.s_hip_c * dA, cT.c2, cA.c2, cT.c0, cA.c0, C.hip_lo, C.hip_hi, act_h, C,
-              Fh, th);
-  // ankle: Aux -> lower leg. axis (cos phi, sin phi, 0), ref e_z
-  const V3 axA = k.axc * cA.c0 + k.axs * cA.c1;
-  const V3 axB = k.axc * cB.c0 + k.axs * cB.c1;
-  V3 Fa, ta;
-  joint_force(r.A, r.B, C.s_ank_p * dA, C.s_ank_c * dB, axA, axB, cA.c2, cB.c2, k.alo, k.ahi, act_a, C, Fa, ta);
-  // impulses: parent gets (-F/m, rp x -F + tau), child gets (F/m, rc x F - tau)
-  V3 dvT = -C.inv_m_torso * Fh;
-  V3 dwT = th - cross(C.s_hip_p * dT, Fh);
-  dvT = quad_sum(dvT);
-  dwT = quad_sum(dwT);
-  const V3 dvA = C.inv_m_leg * (Fh - Fa);
-  const V3 dwA = (cross(C.s_hip_c * dA, Fh) - th) + (ta - cross(C.s_ank_p * dA, Fa));
-  const V3 dvB = C.inv_m_leg * Fa;
-  const V3 dwB = cross(C.s_ank_c * dB, Fa) - ta;
-  // integrators.potential: vel = exp(vdamp h) vel + (dv + g) h ; ang = exp(adamp h) ang + dw h
-  const V3 g = mk(0.f, 0.f, C.gravity_z);
-  r.T.v = C.vel_damp * r.T.v + h * (dvT + g);
-  r.A.v = C.vel_damp * r.A.v + h * (dvA + g);
-  r.B.v = C.vel_damp * r.B.v + h * (dvB + g);
-  r.T.w = C.ang_damp * r.T.w + h * dwT;
-  r.A.w = C.ang_damp * r.A.w + h * dwA;
-  r.B.w = C.ang_damp * r.B.w + h * dwB;
-  // colliders on the post-potential state, then integrators.collision
-  Contact ct;
-  contacts<WALLS>(r, k, C, dA, dB, ct);
-  r.T.v += ct.Tv; r.T.w += ct.Tw;
-  r.A.v += ct.Av; r.A.w += ct.Aw;
-  r.B.v += ct.Bv; r.B.w += ct.Bw;
-  acc.Tv += ct.Tv; acc.Tw += ct.Tw;
-  acc.Av += ct.Av; acc.Aw += ct.Aw;
-  acc.Bv += ct.Bv; acc.Bw += ct.Bw;
+  const V3 xT = cross(r.T.w, dT), xA = cross(r.A.w, dA), xB = cross(r.B.w, dB);
+  // ---- hip: Torso -> Aux, offsets s_hip_p*u / s_hip_c*u, axis e_z, ref -e_x
+  V3 Gh, th;  // Gh = h*F (on the child), th = h*torque (on the parent)
+  {
+    const V3 ep = fma3(-C.s_hip_c, dA, fma3(C.s_hip_p, dT, r.T.p - r.A.p));
+    const V3 ev = fma3(-C.s_hip_c, xA, fma3(C.s_hip_p, xT, r.T.v - r.A.v));
+    Gh = fma3(C.h_sd, ev, C.h_k * ep);
+    // psi = atan2((ref_p x ref_c).axis_p, ref_p.ref_c) with ref = -c0, axis_p = c2_T: the triple product
+    // (c0_T x c0_A).c2_T equals c0_A.(c2_T x c0_T) = c0_A.c1_T
+    const float s = limit_and_actuator(dot(cA.c0, cT.c1), dot(cA.c0, cT.c0), C.hip_lo, C.hip_hi, act_h, C);
+    th = fma3(-C.h_ad, r.T.w - r.A.w, fma3(-s, cT.c2, C.h_k * cross(cT.c2, cA.c2)));
+  }
+  // ---- ankle: Aux -> lower leg, axis (cos phi, sin phi, 0), ref e_z
+  V3 Ga, ta;
+  {
+    const V3 ep = fma3(-C.s_ank_c, dB, fma3(C.s_ank_p, dA, r.A.p - r.B.p));
+    const V3 ev = fma3(-C.s_ank_c, xB, fma3(C.s_ank_p, xA, r.A.v - r.B.v));
+    Ga = fma3(C.h_sd, ev, C.h_k * ep);
+    const V3 axA = k.axc * cA.c0 + k.axs * cA.c1;
+    const V3 axB = k.axc * cB.c0 + k.axs * cB.c1;
+    const V3 nA = k.axs * cA.c0 - k.axc * cA.c1;  // axA x c2_A, so (c2_A x c2_B).axA = c2_B.nA
+    const float s = limit_and_actuator(dot(cB.c2, nA), dot(cA.c2, cB.c2), k.alo, k.ahi, act_a, C);
+    ta = fma3(-C.h_ad, r.A.w - r.B.w, fma3(-s, axA, C.h_k * cross(axA, axB)));
+  }
+  // ---- joint impulses (x h): parent (-F/m, rp x -F + tau), child (F/m, rc x F - tau); torso summed over legs
+  const V3 dvT = quad_sum(-C.inv_m_torso * Gh);
+  const V3 dwT = quad_sum(fma3(-C.s_hip_p, cross(dT, Gh), th));
+  const V3 dvA = C.inv_m_leg * (Gh - Ga);
+  const V3 dwA = cross(dA, fma3(-C.s_ank_p, Ga, C.s_hip_c * Gh)) + (ta - th);
+  const V3 dvB = C.inv_m_leg * Ga;
+  const V3 dwB = fma3(C.s_ank_c, cross(dB, Ga), -ta);
+  // ---- integrators.potential: vel = exp(vdamp h) vel + (dv + g) h ; ang = exp(adamp h) ang + dw h
+  if (C.vel_damp != 1.0f) { r.T.v = C.vel_damp * r.T.v; r.A.v = C.vel_damp * r.A.v; r.B.v = C.vel_damp * r.B.v; }
+  r.T.v = r.T.v + dvT; r.T.v.z += C.h_g;
+  r.A.v = r.A.v + dvA; r.A.v.z += C.h_g;
+  r.B.v = r.B.v + dvB; r.B.v.z += C.h_g;
+  r.T.w = fma3(C.ang_damp, r.T.w, dwT);
+  r.A.w = fma3(C.ang_damp, r.A.w, dwA);
+  r.B.w = fma3(C.ang_damp, r.B.w, dwB);
+  // ---- colliders on the post-potential state + integrators.collision; impulses accumulate into Info.contact
+  contacts<WALLS>(r, C, dA, dB, masks, leg, acc);
 }
 
 // ---- packed state load / store (layout in dev_const.h) -------------------------------------------

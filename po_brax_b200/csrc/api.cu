@@ -237,6 +237,8 @@ static int build_dev_const(const PobraxParams* p, DevConst* Cp, std::vector<uint
   C.r_torso = p->torso_radius; C.r_leg = p->leg_radius;
   C.k_joint = p->joint_stiffness; C.sd_joint = p->joint_spring_damping; C.ad_joint = p->joint_angular_damping;
   C.ls_joint = p->joint_limit_strength; C.act_strength = p->actuator_strength;
+  C.h_k = C.h * C.k_joint; C.h_sd = C.h * C.sd_joint; C.h_ad = C.h * C.ad_joint; C.h_ls = C.h * C.ls_joint;
+  C.h_act = C.h * C.act_strength; C.h_g = C.h * C.gravity_z;
   C.seg_aux = p->aux_length / 2 - p->leg_radius; C.seg_foot = p->foot_length / 2 - p->leg_radius;
   // ---- factor the leg geometry: offsets / capsule ends = scalar * u[l]
   double s_hc = 0, s_ap = 0, s_ac = 0, s_ft = 0, s_ax = 0;

@@ -36,6 +36,7 @@ struct DevConst {
   float h, dt, gravity_z, vel_damp, ang_damp, baumgarte, friction, elasticity;
   float m_torso, m_leg, inv_m_torso, inv_m_leg, r_torso, r_leg;
   float k_joint, sd_joint, ad_joint, ls_joint, act_strength;
+  float h_k, h_sd, h_ad, h_ls, h_act, h_g;   // the same scaled by h (impulses per substep); h_g = h*gravity_z
   // Leg geometry in factored form (validated at create): every joint offset / capsule end of leg l is a
   // uniform scalar times the leg's direction u[l] = (ux, uy, 0) in the body frame.
   float leg_u[4][2];

@@ -60,9 +60,10 @@ struct ObsCols {
 };
 
 // The part of the observation every env shares: [pos0, rot0, joint angles, vel0, ang0, joint vels,
-// clip(contact.vel), clip(contact.ang)] staged into this env's shared-memory row (pre-zeroed).
+// clip(contact.vel), clip(contact.ang)] staged into this env's shared-memory row. The row was zeroed at kernel
+// start and its torso / Aux contact slots already hold the accumulated impulses (ContactAcc): clip in place.
 template <int KIND>
-__device__ __forceinline__ void stage_common_obs(float* row, const Rig& r, const LegK& k, const Contact& ct, int leg,
+__device__ __forceinline__ void stage_common_obs(float* row, const Rig& r, const LegK& k, const ContactAcc& acc, int leg,
                                                  const DevConst& C) {
   using O = ObsCols<KIND>;
   const Cols cT = rot_cols(r.T), cA = rot_cols(r.A), cB = rot_cols(r.B);
@@ -72,7 +73,8 @@ __device__ __forceinline__ void stage_common_obs(float* row, const Rig& r, const
   joint_angle_vel(r.A, r.B, axA, cA.c2, cB.c2, jaa, jva);
   row[O::ja + 2 * leg] = jah; row[O::ja + 2 * leg + 1] = jaa;
   row[O::jv + 2 * leg] = jvh; row[O::jv + 2 * leg + 1] = jva;
-  const int ca = O::cv + 3 * C.nb;
+  float* cv = acc.cv;
+  float* ca = acc.ca;
   if (leg == 0) {
     if (KIND == POBRAX_ANT) {
       row[0] = r.T.p.z;
@@ -82,14 +84,14 @@ __device__ __forceinline__ void stage_common_obs(float* row, const Rig& r, const
     row[O::rot] = r.T.qw; row[O::rot + 1] = r.T.qx; row[O::rot + 2] = r.T.qy; row[O::rot + 3] = r.T.qz;
     row[O::vel] = r.T.v.x; row[O::vel + 1] = r.T.v.y; row[O::vel + 2] = r.T.v.z;
     row[O::ang] = r.T.w.x; row[O::ang + 1] = r.T.w.y; row[O::ang + 2] = r.T.w.z;
-    row[O::cv] = clip1(ct.Tv.x); row[O::cv + 1] = clip1(ct.Tv.y); row[O::cv + 2] = clip1(ct.Tv.z);
-    row[ca] = clip1(ct.Tw.x); row[ca + 1] = clip1(ct.Tw.y); row[ca + 2] = clip1(ct.Tw.z);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { cv[c] = clip1(cv[c]); ca[c] = clip1(ca[c]); }
   }
   const int a = 3 * (1 + 2 * leg), b = 3 * (2 + 2 * leg);
-  row[O::cv + a] = clip1(ct.Av.x); row[O::cv + a + 1] = clip1(ct.Av.y); row[O::cv + a + 2] = clip1(ct.Av.z);
-  row[O::cv + b] = clip1(ct.Bv.x); row[O::cv + b + 1] = clip1(ct.Bv.y); row[O::cv + b + 2] = clip1(ct.Bv.z);
-  row[ca + a] = clip1(ct.Aw.x); row[ca + a + 1] = clip1(ct.Aw.y); row[ca + a + 2] = clip1(ct.Aw.z);
-  row[ca + b] = clip1(ct.Bw.x); row[ca + b + 1] = clip1(ct.Bw.y); row[ca + b + 2] = clip1(ct.Bw.z);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { cv[a + c] = clip1(cv[a + c]); ca[a + c] = clip1(ca[a + c]); }
+  cv[b] = clip1(acc.Bv.x); cv[b + 1] = clip1(acc.Bv.y); cv[b + 2] = clip1(acc.Bv.z);
+  ca[b] = clip1(acc.Bw.x); ca[b + 1] = clip1(acc.Bw.y); ca[b + 2] = clip1(acc.Bw.z);
 }
 
 // AntGatherEnv._get_readings (ant_gather.py:152-181) for this lane's objects (4 per lane), written in
@@ -125,19 +127,31 @@ __device__ __forceinline__ void gather_readings(float* readings, const Body& T, 
 }
 
 // Shared epilogue pieces ------------------------------------------------------------------------------
-// Coalesced write of the warp's 8 staged observation rows; where `from_first` the cached first_obs row.
+// Coalesced write of the warp's 8 staged observation rows (contiguous in obs[N][D]; 8*D floats start at a
+// 16-byte boundary because env0 is a multiple of 8). Rows in `first_mask` are then overwritten from the cached
+// first_obs (rare), rows in `skip_mask` are left untouched (reset_where_done).
 __device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, const float* __restrict__ first_obs,
                                                const float* stage, int D, long long env0, int n_envs, unsigned first_mask,
                                                unsigned skip_mask, int lane) {
-  for (int es = 0; es < 8; ++es) {
-    const long long e = env0 + es;
-    if (e >= n_envs) break;
-    if ((skip_mask >> es) & 1u) continue;
-    const bool ff = (first_mask >> es) & 1u;
-    float* dst = obs + e * D;
-    const float* src = stage + es * D;
-    const float* fsrc = first_obs + e * D;
-    for (int c = lane; c < D; c += 32) dst[c] = ff ? fsrc[c] : src[c];
+  const int rows = (int)min((long long)8, (long long)n_envs - env0);
+  if (rows <= 0) return;
+  float* dst = obs + env0 * D;
+  if (skip_mask == 0u) {
+    const int n4 = (rows * D) >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(stage);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = lane; i < n4; i += 32) d4[i] = s4[i];
+    for (int i = 4 * n4 + lane; i < rows * D; i += 32) dst[i] = stage[i];
+  } else {
+    for (int es = 0; es < rows; ++es)
+      if (!((skip_mask >> es) & 1u))
+        for (int c = lane; c < D; c += 32) dst[es * D + c] = stage[es * D + c];
+  }
+  if (first_mask != 0u) {
+    __syncwarp();
+    for (int es = 0; es < rows; ++es)
+      if ((first_mask >> es) & 1u)
+        for (int c = lane; c < D; c += 32) dst[es * D + c] = first_obs[(env0 + es) * D + c];
   }
 }
 
@@ -158,6 +172,7 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
   float* row = stage + es * D;
 
   for (int i = lane; i < 8 * D; i += 32) stage[i] = 0.0f;
+  __syncwarp();
 
   const LegK k = leg_consts(C, leg);
   Rig r;
@@ -168,14 +183,16 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
   if (C.auto_reset == POBRAX_AUTORESET_CACHED && done_prev != 0.0f) steps = 0.0f;  // AutoResetWrapper.step head
   const float x_before = r.T.p.x;
 
-  Contact acc;
-  acc.Tv = acc.Tw = acc.Av = acc.Aw = acc.Bv = acc.Bw = mk(0.f, 0.f, 0.f);
+  ContactAcc acc;
+  acc.Bv = acc.Bw = mk(0.f, 0.f, 0.f);
+  acc.cv = row + ObsCols<KIND>::cv;
+  acc.ca = acc.cv + 3 * C.nb;
   if (KIND != POBRAX_ANT && C.n_walls > 0) {
 #pragma unroll 1
-    for (int s = 0; s < C.substeps; ++s) substep<true>(r, k, act.x, act.y, C, acc);
+    for (int s = 0; s < C.substeps; ++s) substep<true>(r, k, act.x, act.y, C, leg, acc);
   } else {
 #pragma unroll 1
-    for (int s = 0; s < C.substeps; ++s) substep<false>(r, k, act.x, act.y, C, acc);
+    for (int s = 0; s < C.substeps; ++s) substep<false>(r, k, act.x, act.y, C, leg, acc);
   }
 
   __syncwarp();
@@ -192,8 +209,10 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
   if (KIND == POBRAX_ANT) {
     const float forward = __fdiv_rn(__fsub_rn(r.T.p.x, x_before), C.dt);
     const float ctrl = 0.5f * quad_sum(act.x * act.x + act.y * act.y);
-    auto sq3 = [](V3 v) { const float a = clip1(v.x), b = clip1(v.y), c = clip1(v.z); return a * a + b * b + c * c; };
-    const float contact = 0.5e-3f * (sq3(acc.Tv) + quad_sum(sq3(acc.Av) + sq3(acc.Bv)));
+    // 0.5e-3 * sum over bodies of |clip(contact.vel)|^2, read back from the staged (clipped) row
+    __syncwarp();
+    auto sq3 = [](const float* v) { return v[0] * v[0] + v[1] * v[1] + v[2] * v[2]; };
+    const float contact = 0.5e-3f * (sq3(acc.cv) + quad_sum(sq3(acc.cv + 3 * (1 + 2 * leg)) + sq3(acc.cv + 3 * (2 + 2 * leg))));
     reward = ((forward - ctrl) - contact) + 1.0f;
     done = dead;
     m0 = ctrl; m1 = contact; m2 = forward; m3 = 1.0f;
@@ -395,6 +414,7 @@ reset_kernel(const __grid_constant__ DevConst C, const PobraxState S, const uint
   uint32_t* sort_keys = reinterpret_cast<uint32_t*>(smem + (size_t)(kThreads / 32) * 8 * D) +
                         (size_t)(warp * 8 + es) * (KIND == POBRAX_ANT_GATHER ? C.n_grid : 0);
   for (int i = lane; i < 8 * D; i += 32) stage[i] = 0.0f;
+  __syncwarp();
 
   const bool active = !only_done || S.done[e] != 0.0f;  // uniform over the quad
   const LegK k = leg_consts(C, leg);
@@ -501,13 +521,22 @@ reset_kernel(const __grid_constant__ DevConst C, const PobraxState S, const uint
     }
   }
 
-  // ---- info = sys.info(qp): one collider evaluation, no integration
-  Contact ct;
+  // ---- info = sys.info(qp): one collider evaluation, no integration (the velocity update is discarded)
+  ContactAcc ct;
+  ct.Bv = ct.Bw = mk(0.f, 0.f, 0.f);
+  ct.cv = row + ObsCols<KIND>::cv;
+  ct.ca = ct.cv + 3 * C.nb;
   {
     const Cols cA = rot_cols(r.A), cB = rot_cols(r.B);
     const V3 dA = k.ux * cA.c0 + k.uy * cA.c1, dB = k.ux * cB.c0 + k.uy * cB.c1;
-    if (KIND != POBRAX_ANT && C.n_walls > 0) contacts<true>(r, k, C, dA, dB, ct);
-    else contacts<false>(r, k, C, dA, dB, ct);
+    Rig tmp = r;
+    if (KIND != POBRAX_ANT && C.n_walls > 0) {
+      const unsigned masks = wall_mask_at(C, r.T.p.x, r.T.p.y) | (wall_mask_at(C, r.A.p.x, r.A.p.y) << 8) |
+                             (wall_mask_at(C, r.B.p.x, r.B.p.y) << 16);
+      contacts<true>(tmp, C, dA, dB, masks, leg, ct);
+    } else {
+      contacts<false>(tmp, C, dA, dB, 0u, leg, ct);
+    }
   }
   __syncwarp();
   stage_common_obs<KIND>(row, r, k, ct, leg, C);

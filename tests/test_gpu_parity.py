@@ -198,17 +198,23 @@ def test_episode_and_cached_autoreset(kind):
     env = _make(kind, n, episode_length=L, auto_reset=True)
     cs = env.reset(keys)
     rng = tf.prng_key(2)
+    oenv.env.sys.track_margin = True
+    dirty = np.zeros(n, bool)  # envs whose current episode went through a rounding-ambiguous branch (see _parity.py)
     for t in range(T):
         rng, a = P.actions_for(rng, n)
+        oenv.env.sys.margin = None
         s = oenv.step(s, a)
         cs = env.step(cs, torch.as_tensor(a, device='cuda'))
+        dirty |= oenv.env.sys.margin <= P.BRANCH_MARGIN
         assert np.array_equal(P.t2n(cs.info['steps']), s.info['steps']), f't={t}'
-        assert np.array_equal(P.t2n(cs.done), np.asarray(s.done, np.float32)), f't={t}'
-        assert np.array_equal(P.t2n(cs.info['truncation']), s.info['truncation']), f't={t}'
+        ok = ~dirty
+        assert np.array_equal(P.t2n(cs.done)[ok], np.asarray(s.done, np.float32)[ok]), f't={t}'
+        assert np.array_equal(P.t2n(cs.info['truncation'])[ok], s.info['truncation'][ok]), f't={t}'
         # within an episode of 4 steps free-running drift stays far below the gates; after a reset both sides
         # return to the cached first state
-        P.assert_qp_close(cs.qp, s.qp, f'{kind} autoreset t={t}', vel_atol=5e-3, pos_scale=10.0)
-    assert float(P.t2n(cs.done).sum()) >= 0
+        P.assert_qp_close(cs.qp, s.qp, f'{kind} autoreset t={t}', vel_atol=5e-3, pos_scale=10.0, rows=ok)
+        dirty &= ~np.asarray(s.done, bool)  # episode over: both sides are back on the cached first state
+    assert (~dirty).mean() > 0.5
 
 
 @pytest.mark.parametrize('kind', ['ant_heavenhell', 'ant_gather', 'ant_tag'])

@@ -197,13 +197,14 @@ __device__ __noinline__ Imp contact_general(V3 p, V3 e, V3 v, V3 w, float rad, f
   return impulse(rel, v + cross(w, rel), n, pen, inv_m, baumgarte, friction, elasticity);
 }
 
-// Candidate walls of a body centred at (x, y): bit w set <=> wall w is within the largest capsule reach of the
-// table cell (exact rectangle-rectangle distance, so culling stays exact); every wall outside the table.
-__device__ __forceinline__ unsigned wall_mask_at(const DevConst& C, float x, float y) {
+// Candidate walls of a body centred at (x, y): bit w of the byte set <=> wall w is within that body type's
+// reach of the table cell (exact rectangle-rectangle distance in xy, so culling stays exact). One table per
+// body type `kind` (0 torso sphere, 1 Aux capsule, 2 lower-leg capsule); outside the table: every wall.
+__device__ __forceinline__ unsigned wall_mask_at(const DevConst& C, int kind, float x, float y) {
   const float fx = (x - C.sdf_x0) * C.sdf_inv_cell, fy = (y - C.sdf_y0) * C.sdf_inv_cell;
   const int ix = min(max((int)fx, 0), C.sdf_nx - 1);
   const int iy = min(max((int)fy, 0), C.sdf_ny - 1);
-  return __ldg(C.wall_mask + iy * C.sdf_nx + ix);
+  return __ldg(C.wall_mask + kind * C.sdf_plane + iy * C.sdf_nx + ix);
 }
 
 // Per-lane constants of leg l.
@@ -238,6 +239,33 @@ __device__ __forceinline__ float quad_sum(float x) {
 }
 __device__ __forceinline__ V3 quad_sum(V3 a) { return mk(quad_sum(a.x), quad_sum(a.y), quad_sum(a.z)); }
 
+// The Arena collider group of one body: capsule (segment p + e .. p - e, radius rad) vs its candidate boxes.
+// Contacts are summed and divided by (1e-8 + #contacts with a non-zero dv). A box whose closest point to the
+// capsule centre is further than `reach` (half segment + radius) cannot touch: skipped exactly.
+__device__ __forceinline__ Imp wall_group(const Body& b, V3 e, float rad, float reach, float inv_m, unsigned m,
+                                          const DevConst& C) {
+  Imp o;
+  o.dv = o.dw = mk(0.f, 0.f, 0.f);
+  o.hit = 0.0f;
+  const float reach2 = reach * reach;
+  do {
+    const int w = __ffs(m) - 1;
+    m &= m - 1;
+    const float4 l4 = C.wall_box[w][0], h4 = C.wall_box[w][1];
+    const V3 lo = mk(l4.x, l4.y, l4.z), hi = mk(h4.x, h4.y, h4.z);
+    const V3 cd = b.p - clamp3(b.p, lo, hi);
+    if (dot(cd, cd) <= reach2) {
+      const Imp c = contact_general(b.p, e, b.v, b.w, rad, inv_m, lo, hi, 0, C.baumgarte, C.friction, C.elasticity);
+      o.dv += c.dv; o.dw += c.dw; o.hit += c.hit;
+    }
+  } while (m);
+  if (o.hit > 1.0f) {  // (1e-8 + 1) == 1 in float32: only a multi-contact group divides
+    const float inv = 1.0f / (1e-8f + o.hit);
+    o.dv = inv * o.dv; o.dw = inv * o.dw;
+  }
+  return o;
+}
+
 // Σ colliders.apply(qp) for the lane's bodies -- ground (torso sphere, foot end) + Arena walls (all three) --
 // evaluated on the state in `r`; then integrators.collision (vel += dv, ang += dw) and the Info.contact sums.
 // Every contact is evaluated on the same (pre-collision) state: a body's impulses are applied only after all
@@ -255,44 +283,22 @@ __device__ __forceinline__ void contacts(Rig& r, const DevConst& C, V3 dA, V3 dB
     gT = contact_general(r.T.p, zero, r.T.v, r.T.w, C.r_torso, C.inv_m_torso, zero, zero, 1, C.baumgarte, C.friction,
                          C.elasticity);
   if (WALLS && masks != 0u) {
-#pragma unroll 1
-    for (int i = 0; i < 3; ++i) {  // one copy of the pair loop; operands selected per body
-      unsigned m = (masks >> (8 * i)) & 0xffu;
-      if (m == 0u) continue;
-      const V3 p = i == 0 ? r.T.p : (i == 1 ? r.A.p : r.B.p);
-      const float reach = (i == 0 ? C.r_torso : (i == 1 ? C.seg_aux + C.r_leg : C.seg_foot + C.r_leg)) + 1e-4f;
-      V3 sv = zero, sw = zero;
-      float cnt = 0.0f;
-      bool any = false;
-      while (m) {
-        const int w = __ffs(m) - 1;
-        m &= m - 1;
-        const V3 lo = mk(C.wall_lo[w][0], C.wall_lo[w][1], C.wall_lo[w][2]);
-        const V3 hi = mk(C.wall_hi[w][0], C.wall_hi[w][1], C.wall_hi[w][2]);
-        const V3 cd = p - clamp3(p, lo, hi);
-        if (dot(cd, cd) > reach * reach) continue;  // exact: further than the capsule's reach => pen <= 0
-        const V3 v = i == 0 ? r.T.v : (i == 1 ? r.A.v : r.B.v);
-        const V3 wv = i == 0 ? r.T.w : (i == 1 ? r.A.w : r.B.w);
-        const V3 e = i == 0 ? zero : (i == 1 ? C.s_aux * dA : C.s_foot * dB);
-        const Imp c = contact_general(p, e, v, wv, i == 0 ? C.r_torso : C.r_leg, i == 0 ? C.inv_m_torso : C.inv_m_leg,
-                                      lo, hi, 0, C.baumgarte, C.friction, C.elasticity);
-        sv += c.dv; sw += c.dw; cnt += c.hit;
-        any = true;
-      }
-      if (any) {
-        const float inv = 1.0f / (1e-8f + cnt);
-        const V3 dv = inv * sv, dw = inv * sw;
-        if (i == 0) {
-          r.T.v += dv; r.T.w += dw;
-          if (leg == 0) { row_add(acc.cv, 0, dv); row_add(acc.ca, 0, dw); }
-        } else if (i == 1) {
-          r.A.v += dv; r.A.w += dw;
-          row_add(acc.cv, 1 + 2 * leg, dv); row_add(acc.ca, 1 + 2 * leg, dw);
-        } else {
-          r.B.v += dv; r.B.w += dw;
-          acc.Bv += dv; acc.Bw += dw;
-        }
-      }
+    // per body: exact centre-distance test of each candidate wall inline, the narrow phase out of line
+    const unsigned mT = masks & 0xffu, mA = (masks >> 8) & 0xffu, mB = masks >> 16;
+    if (mT != 0u) {
+      const Imp c = wall_group(r.T, zero, C.r_torso, C.r_torso + 1e-4f, C.inv_m_torso, mT, C);
+      r.T.v += c.dv; r.T.w += c.dw;
+      if (leg == 0) { row_add(acc.cv, 0, c.dv); row_add(acc.ca, 0, c.dw); }
+    }
+    if (mA != 0u) {
+      const Imp c = wall_group(r.A, C.s_aux * dA, C.r_leg, C.seg_aux + C.r_leg + 1e-4f, C.inv_m_leg, mA, C);
+      r.A.v += c.dv; r.A.w += c.dw;
+      row_add(acc.cv, 1 + 2 * leg, c.dv); row_add(acc.ca, 1 + 2 * leg, c.dw);
+    }
+    if (mB != 0u) {
+      const Imp c = wall_group(r.B, C.s_foot * dB, C.r_leg, C.seg_foot + C.r_leg + 1e-4f, C.inv_m_leg, mB, C);
+      r.B.v += c.dv; r.B.w += c.dw;
+      acc.Bv += c.dv; acc.Bw += c.dw;
     }
   }
   if (hitB) {
@@ -316,8 +322,8 @@ __device__ __forceinline__ void substep(Rig& r, const LegK& k, float act_h, floa
   // positions are final for this substep: fetch the candidate-wall masks now, use them after the joint math
   unsigned masks = 0u;
   if (WALLS)
-    masks = wall_mask_at(C, r.T.p.x, r.T.p.y) | (wall_mask_at(C, r.A.p.x, r.A.p.y) << 8) |
-            (wall_mask_at(C, r.B.p.x, r.B.p.y) << 16);
+    masks = wall_mask_at(C, 0, r.T.p.x, r.T.p.y) | (wall_mask_at(C, 1, r.A.p.x, r.A.p.y) << 8) |
+            (wall_mask_at(C, 2, r.B.p.x, r.B.p.y) << 16);
   const Cols cT = rot_cols(r.T), cA = rot_cols(r.A), cB = rot_cols(r.B);
   const V3 dT = k.ux * cT.c0 + k.uy * cT.c1;  // R_T u: every lever arm of the leg is a scalar times dT / dA / dB
   const V3 dA = k.ux * cA.c0 + k.uy * cA.c1;

@@ -287,42 +287,48 @@ static int build_dev_const(const PobraxParams* p, DevConst* Cp, std::vector<uint
   // ---- walls + conservative distance field
   C.n_walls = (p->env_kind == POBRAX_ANT) ? 0 : p->num_walls;
   C.arena_z = p->arena_z;
-  for (int w = 0; w < C.n_walls; ++w)
+  float wlo[pobrax::kMaxWalls][3], whi[pobrax::kMaxWalls][3];
+  for (int w = 0; w < C.n_walls; ++w) {
     for (int c = 0; c < 3; ++c) {
       if (!(p->wall_lo[w][c] <= p->wall_hi[w][c])) return fail("wall box with lo > hi");
-      C.wall_lo[w][c] = p->wall_lo[w][c]; C.wall_hi[w][c] = p->wall_hi[w][c];
+      wlo[w][c] = p->wall_lo[w][c]; whi[w][c] = p->wall_hi[w][c];
     }
+    C.wall_box[w][0] = make_float4(wlo[w][0], wlo[w][1], wlo[w][2], 0.f);
+    C.wall_box[w][1] = make_float4(whi[w][0], whi[w][1], whi[w][2], 0.f);
+  }
   sdf->clear();
   if (C.n_walls > 0) {
-    const double cell = 0.25, margin = 2.0;
+    const double cell = 0.125, margin = 2.0;
     double x0 = 1e30, y0 = 1e30, x1 = -1e30, y1 = -1e30;
     for (int w = 0; w < C.n_walls; ++w) {
-      x0 = std::fmin(x0, C.wall_lo[w][0]); y0 = std::fmin(y0, C.wall_lo[w][1]);
-      x1 = std::fmax(x1, C.wall_hi[w][0]); y1 = std::fmax(y1, C.wall_hi[w][1]);
+      x0 = std::fmin(x0, wlo[w][0]); y0 = std::fmin(y0, wlo[w][1]);
+      x1 = std::fmax(x1, whi[w][0]); y1 = std::fmax(y1, whi[w][1]);
     }
     x0 -= margin; y0 -= margin; x1 += margin; y1 += margin;
     const int nx = (int)std::ceil((x1 - x0) / cell), ny = (int)std::ceil((y1 - y0) / cell);
-    if (nx <= 2 || ny <= 2 || (long long)nx * ny > (1 << 22)) return fail("wall extent unsupported (distance field too large)");
-    // Bit w of a cell: some point of the cell is within `reach` (largest capsule bounding radius, plus slack
-    // for the float cell lookup) of wall w in the xy-plane. Border cells (and everything outside the table,
-    // which clamps onto them) list every wall.
+    if (nx <= 2 || ny <= 2 || (long long)nx * ny > (1 << 22)) return fail("wall extent unsupported (mask table too large)");
+    // Bit w of a cell (per body type): some point of the cell is within that body's reach (capsule half
+    // segment + radius, plus slack for the float cell lookup) of wall w in the xy-plane. Border cells (and
+    // everything outside the table, which clamps onto them) list every wall.
     const uint8_t all = (uint8_t)((1u << C.n_walls) - 1u);
-    sdf->assign((size_t)nx * ny, all);
-    const double reach = std::fmax(C.r_torso, std::fmax(C.seg_aux, C.seg_foot) + C.r_leg) + 1e-3;
-    for (int iy = 1; iy < ny - 1; ++iy)
-      for (int ix = 1; ix < nx - 1; ++ix) {
-        const double cx0 = x0 + ix * cell - 1e-4, cx1 = x0 + (ix + 1) * cell + 1e-4;
-        const double cy0 = y0 + iy * cell - 1e-4, cy1 = y0 + (iy + 1) * cell + 1e-4;
-        uint8_t m = 0;
-        for (int w = 0; w < C.n_walls; ++w) {
-          const double dx = std::fmax(std::fmax(C.wall_lo[w][0] - cx1, 0.0), cx0 - C.wall_hi[w][0]);
-          const double dy = std::fmax(std::fmax(C.wall_lo[w][1] - cy1, 0.0), cy0 - C.wall_hi[w][1]);
-          if (std::sqrt(dx * dx + dy * dy) <= reach) m |= (uint8_t)(1u << w);
+    const size_t plane = (size_t)nx * ny;
+    sdf->assign(3 * plane, all);
+    const double reach[3] = {C.r_torso + 2e-3, C.seg_aux + C.r_leg + 2e-3, C.seg_foot + C.r_leg + 2e-3};
+    for (int k = 0; k < 3; ++k)
+      for (int iy = 1; iy < ny - 1; ++iy)
+        for (int ix = 1; ix < nx - 1; ++ix) {
+          const double cx0 = x0 + ix * cell - 1e-4, cx1 = x0 + (ix + 1) * cell + 1e-4;
+          const double cy0 = y0 + iy * cell - 1e-4, cy1 = y0 + (iy + 1) * cell + 1e-4;
+          uint8_t m = 0;
+          for (int w = 0; w < C.n_walls; ++w) {
+            const double dx = std::fmax(std::fmax(wlo[w][0] - cx1, 0.0), cx0 - whi[w][0]);
+            const double dy = std::fmax(std::fmax(wlo[w][1] - cy1, 0.0), cy0 - whi[w][1]);
+            if (std::sqrt(dx * dx + dy * dy) <= reach[k]) m |= (uint8_t)(1u << w);
+          }
+          (*sdf)[k * plane + (size_t)iy * nx + ix] = m;
         }
-        (*sdf)[(size_t)iy * nx + ix] = m;
-      }
     C.sdf_x0 = (float)x0; C.sdf_y0 = (float)y0; C.sdf_inv_cell = (float)(1.0 / cell);
-    C.sdf_nx = nx; C.sdf_ny = ny;
+    C.sdf_nx = nx; C.sdf_ny = ny; C.sdf_plane = (int)plane;
   }
   // ---- task
   C.dying_cost = p->dying_cost; C.visible_radius = p->visible_radius;

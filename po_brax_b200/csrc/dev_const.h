@@ -2,6 +2,7 @@
 // Passed to every kernel by value as a __grid_constant__ parameter (constant bank; uniform loads).
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>
 
 namespace pobrax {
 
@@ -48,8 +49,9 @@ struct DevConst {
   float ank_lo[4], ank_hi[4];
   float hip_default, ank_default[4];         // default_angle(): limit midpoints
   // walls: axis-aligned boxes in world coordinates + a per-cell candidate mask for exact culling
-  float wall_lo[kMaxWalls][3], wall_hi[kMaxWalls][3];
-  const uint8_t* wall_mask;                  // [sdf_ny][sdf_nx] candidate-wall bit mask of each xy cell (exact culling)
+  float4 wall_box[kMaxWalls][2];             // (lo.xyz, -), (hi.xyz, -): 16-byte aligned for vector constant loads
+  const uint8_t* wall_mask;                  // [3 body types][sdf_ny][sdf_nx] candidate-wall bit mask of each xy cell
+  int32_t sdf_plane;                         // sdf_nx * sdf_ny
   float sdf_x0, sdf_y0, sdf_inv_cell;
   int32_t sdf_nx, sdf_ny;
   // task

@@ -531,8 +531,8 @@ reset_kernel(const __grid_constant__ DevConst C, const PobraxState S, const uint
     const V3 dA = k.ux * cA.c0 + k.uy * cA.c1, dB = k.ux * cB.c0 + k.uy * cB.c1;
     Rig tmp = r;
     if (KIND != POBRAX_ANT && C.n_walls > 0) {
-      const unsigned masks = wall_mask_at(C, r.T.p.x, r.T.p.y) | (wall_mask_at(C, r.A.p.x, r.A.p.y) << 8) |
-                             (wall_mask_at(C, r.B.p.x, r.B.p.y) << 16);
+      const unsigned masks = wall_mask_at(C, 0, r.T.p.x, r.T.p.y) | (wall_mask_at(C, 1, r.A.p.x, r.A.p.y) << 8) |
+                             (wall_mask_at(C, 2, r.B.p.x, r.B.p.y) << 16);
       contacts<true>(tmp, C, dA, dB, masks, leg, ct);
     } else {
       contacts<false>(tmp, C, dA, dB, 0u, leg, ct);

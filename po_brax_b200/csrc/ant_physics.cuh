@@ -118,28 +118,25 @@ __device__ __forceinline__ Imp impulse(V3 rel, V3 v, V3 n, float pen, float inv_
 }
 
 // Capsule-end vs ground plane (normal +z through the origin) for the foot, the one contact that is live on
-// most substeps: `impulse` written out for n = e_z. e = world-frame offset of the capsule end from the body.
-__device__ __forceinline__ bool foot_ground(const Body& b, V3 e, float r, float inv_m, const DevConst& C, V3& dv,
+// most substeps: `impulse` written out for n = e_z and branch-free (masked like the reference's where()s), so
+// the substep loop has no divergent region for it. e = world-frame offset of the capsule end from the body.
+__device__ __forceinline__ void foot_ground(const Body& b, V3 e, float r, float inv_m, const DevConst& C, V3& dv,
                                             V3& dw) {
   const float pen = r - (b.p.z + e.z);
-  if (!(pen > 0.0f)) return false;
   const float rx = e.x, ry = e.y, rz = e.z - r;
   const float vx = b.v.x + (b.w.y * rz - b.w.z * ry);
   const float vy = b.v.y + (b.w.z * rx - b.w.x * rz);
   const float nv = b.v.z + (b.w.x * ry - b.w.y * rx);
   const float rden = __fdividef(1.0f, inv_m + (rx * rx + ry * ry));
   const float J = (C.baumgarte * pen - (1.0f + C.elasticity) * nv) * rden;
-  if (!((nv < 0.0f) && (J > 0.0f))) return false;
-  dv = mk(0.f, 0.f, inv_m * J);
-  dw = mk(ry * J, -rx * J, 0.f);
+  const bool apply_n = (pen > 0.0f) && (nv < 0.0f) && (J > 0.0f);
+  const float Jn = apply_n ? J : 0.0f;
   const float nd = sqrtf(vx * vx + vy * vy);
-  if (nd > 0.01f) {
-    const float c = __fdividef(-fminf(nd * rden, C.friction * J), 1e-6f + nd);
-    const float jx = c * vx, jy = c * vy;
-    dv.x = inv_m * jx; dv.y = inv_m * jy;
-    dw.x -= rz * jy; dw.y += rz * jx; dw.z = rx * jy - ry * jx;
-  }
-  return true;
+  const float cd = __fdividef(-fminf(nd * rden, C.friction * J), 1e-6f + nd);
+  const float c = (apply_n && nd > 0.01f) ? cd : 0.0f;
+  const float jx = c * vx, jy = c * vy;
+  dv = mk(inv_m * jx, inv_m * jy, inv_m * Jn);
+  dw = mk(ry * Jn - rz * jy, rz * jx - rx * Jn, rx * jy - ry * jx);
 }
 
 __device__ __forceinline__ V3 clamp3(V3 p, V3 lo, V3 hi) {
@@ -172,8 +169,8 @@ __device__ __forceinline__ float seg_box_t(V3 a, V3 d, V3 lo, V3 hi) {
 //  plane = 0: capsule (segment p + e .. p - e, radius rad) vs the axis-aligned Arena box [lo, hi]: one contact at
 //             the closest box point, normal (seg_pt - box_pt)/(1e-6 + d), penetration rad - d;
 //  plane = 1: sphere (e = 0) vs the ground plane z = 0 (the torso's capsule_plane candidate).
-__device__ __noinline__ Imp contact_general(V3 p, V3 e, V3 v, V3 w, float rad, float inv_m, V3 lo, V3 hi, int plane,
-                                            float baumgarte, float friction, float elasticity) {
+__device__ __forceinline__ Imp contact_general(V3 p, V3 e, V3 v, V3 w, float rad, float inv_m, V3 lo, V3 hi, int plane,
+                                               float baumgarte, float friction, float elasticity) {
   if (plane) {
     const V3 rel = mk(0.f, 0.f, -rad);
     return impulse(rel, v + cross(w, rel), mk(0.f, 0.f, 1.f), rad - p.z, inv_m, baumgarte, friction, elasticity);
@@ -239,23 +236,29 @@ __device__ __forceinline__ float quad_sum(float x) {
 }
 __device__ __forceinline__ V3 quad_sum(V3 a) { return mk(quad_sum(a.x), quad_sum(a.y), quad_sum(a.z)); }
 
-// The Arena collider group of one body: capsule (segment p + e .. p - e, radius rad) vs its candidate boxes.
-// Contacts are summed and divided by (1e-8 + #contacts with a non-zero dv). A box whose closest point to the
-// capsule centre is further than `reach` (half segment + radius) cannot touch: skipped exactly.
-__device__ __forceinline__ Imp wall_group(const Body& b, V3 e, float rad, float reach, float inv_m, unsigned m,
-                                          const DevConst& C) {
+// The rare collider groups of one body, out of line (one copy, register-passed arguments) so the substep loop
+// stays small enough for the instruction cache:
+//  m != 0: the Arena group -- capsule (segment p + e .. p - e, radius rad) vs its candidate boxes (bit mask m,
+//          boxes in global memory). Contacts are summed and divided by (1e-8 + #contacts with a non-zero dv).
+//          A box whose closest point to the capsule centre is further than sqrt(reach2) (half segment +
+//          radius) cannot touch: skipped exactly.
+//  m == 0: the torso's ground-plane candidate (sphere vs z = 0).
+__device__ __noinline__ Imp rare_group(V3 p, V3 e, V3 v, V3 w, float rad, float reach2, float inv_m, unsigned m,
+                                       const float4* __restrict__ walls, float baumgarte, float friction,
+                                       float elasticity) {
+  const V3 zero = mk(0.f, 0.f, 0.f);
+  if (m == 0u) return contact_general(p, zero, v, w, rad, inv_m, zero, zero, 1, baumgarte, friction, elasticity);
   Imp o;
-  o.dv = o.dw = mk(0.f, 0.f, 0.f);
+  o.dv = o.dw = zero;
   o.hit = 0.0f;
-  const float reach2 = reach * reach;
   do {
-    const int w = __ffs(m) - 1;
+    const int k = __ffs(m) - 1;
     m &= m - 1;
-    const float4 l4 = C.wall_box[w][0], h4 = C.wall_box[w][1];
+    const float4 l4 = __ldg(walls + 2 * k), h4 = __ldg(walls + 2 * k + 1);
     const V3 lo = mk(l4.x, l4.y, l4.z), hi = mk(h4.x, h4.y, h4.z);
-    const V3 cd = b.p - clamp3(b.p, lo, hi);
+    const V3 cd = p - clamp3(p, lo, hi);
     if (dot(cd, cd) <= reach2) {
-      const Imp c = contact_general(b.p, e, b.v, b.w, rad, inv_m, lo, hi, 0, C.baumgarte, C.friction, C.elasticity);
+      const Imp c = contact_general(p, e, v, w, rad, inv_m, lo, hi, 0, baumgarte, friction, elasticity);
       o.dv += c.dv; o.dw += c.dw; o.hit += c.hit;
     }
   } while (m);
@@ -266,64 +269,73 @@ __device__ __forceinline__ Imp wall_group(const Body& b, V3 e, float rad, float 
   return o;
 }
 
+__device__ __forceinline__ Imp wall_group(const Body& b, V3 e, float rad, float reach, float inv_m, unsigned m,
+                                          const DevConst& C) {
+  return rare_group(b.p, e, b.v, b.w, rad, reach * reach, inv_m, m, C.walls, C.baumgarte, C.friction, C.elasticity);
+}
+
 // Σ colliders.apply(qp) for the lane's bodies -- ground (torso sphere, foot end) + Arena walls (all three) --
 // evaluated on the state in `r`; then integrators.collision (vel += dv, ang += dw) and the Info.contact sums.
 // Every contact is evaluated on the same (pre-collision) state: a body's impulses are applied only after all
 // of that body's contacts have been evaluated. A body has at most one ground candidate, so the ground
 // group's "divide by the active count" is a no-op; the wall group divides per body.
 template <bool WALLS>
-__device__ __forceinline__ void contacts(Rig& r, const DevConst& C, V3 dA, V3 dB, unsigned masks, int leg,
-                                         ContactAcc& acc) {
+__device__ __forceinline__ void contacts(Rig& r, const DevConst& C, V3 dA, V3 dB, unsigned mT, unsigned mA,
+                                         unsigned mB, int leg, ContactAcc& acc) {
   V3 gv, gw;
-  const bool hitB = foot_ground(r.B, C.s_foot * dB, C.r_leg, C.inv_m_leg, C, gv, gw);
-  const V3 zero = mk(0.f, 0.f, 0.f);
-  Imp gT;
+  foot_ground(r.B, C.s_foot * dB, C.r_leg, C.inv_m_leg, C, gv, gw);
   const bool hitT = C.r_torso - r.T.p.z > 0.0f;
-  if (hitT)
-    gT = contact_general(r.T.p, zero, r.T.v, r.T.w, C.r_torso, C.inv_m_torso, zero, zero, 1, C.baumgarte, C.friction,
-                         C.elasticity);
-  if (WALLS && masks != 0u) {
-    // per body: exact centre-distance test of each candidate wall inline, the narrow phase out of line
-    const unsigned mT = masks & 0xffu, mA = (masks >> 8) & 0xffu, mB = masks >> 16;
-    if (mT != 0u) {
-      const Imp c = wall_group(r.T, zero, C.r_torso, C.r_torso + 1e-4f, C.inv_m_torso, mT, C);
-      r.T.v += c.dv; r.T.w += c.dw;
-      if (leg == 0) { row_add(acc.cv, 0, c.dv); row_add(acc.ca, 0, c.dw); }
+  if (hitT || (WALLS && (mT | mA | mB) != 0u)) {  // the one divergent region of the substep (rare)
+    const V3 zero = mk(0.f, 0.f, 0.f);
+    if (hitT || mT != 0u) {
+      Imp t;
+      t.dv = t.dw = zero;
+      if (hitT)
+        t = rare_group(r.T.p, zero, r.T.v, r.T.w, C.r_torso, 0.0f, C.inv_m_torso, 0u, C.walls, C.baumgarte, C.friction,
+                       C.elasticity);
+      if (WALLS && mT != 0u) {
+        const Imp c = wall_group(r.T, zero, C.r_torso, C.r_torso + 1e-4f, C.inv_m_torso, mT, C);
+        t.dv += c.dv; t.dw += c.dw;
+      }
+      r.T.v += t.dv; r.T.w += t.dw;
+      if (leg == 0) { row_add(acc.cv, 0, t.dv); row_add(acc.ca, 0, t.dw); }
     }
-    if (mA != 0u) {
+    if (WALLS && mA != 0u) {
       const Imp c = wall_group(r.A, C.s_aux * dA, C.r_leg, C.seg_aux + C.r_leg + 1e-4f, C.inv_m_leg, mA, C);
       r.A.v += c.dv; r.A.w += c.dw;
       row_add(acc.cv, 1 + 2 * leg, c.dv); row_add(acc.ca, 1 + 2 * leg, c.dw);
     }
-    if (mB != 0u) {
+    if (WALLS && mB != 0u) {
       const Imp c = wall_group(r.B, C.s_foot * dB, C.r_leg, C.seg_foot + C.r_leg + 1e-4f, C.inv_m_leg, mB, C);
       r.B.v += c.dv; r.B.w += c.dw;
       acc.Bv += c.dv; acc.Bw += c.dw;
     }
   }
-  if (hitB) {
-    r.B.v += gv; r.B.w += gw;
-    acc.Bv += gv; acc.Bw += gw;
-  }
-  if (hitT) {
-    r.T.v += gT.dv; r.T.w += gT.dw;
-    if (leg == 0) { row_add(acc.cv, 0, gT.dv); row_add(acc.ca, 0, gT.dw); }
-  }
+  r.B.v += gv; r.B.w += gw;
+  acc.Bv += gv; acc.Bw += gw;
 }
 
-// One physics substep for the lane's three bodies. act_h / act_a: hip / ankle actions.
-// All impulses carry the factor h (C.h_k = h*stiffness, ...), so `potential` is a plain add.
+// integrators.kinetic for the lane's bodies + (walls) the candidate-wall masks of the new positions. Run ahead
+// of the substep that consumes them, so the three table loads are in flight during the joint math.
 template <bool WALLS>
-__device__ __forceinline__ void substep(Rig& r, const LegK& k, float act_h, float act_a, const DevConst& C, int leg,
-                                        ContactAcc& acc) {
+__device__ __forceinline__ void advance(Rig& r, const DevConst& C, unsigned& mT, unsigned& mA, unsigned& mB) {
   kinetic(r.T, C.h);
   kinetic(r.A, C.h);
   kinetic(r.B, C.h);
-  // positions are final for this substep: fetch the candidate-wall masks now, use them after the joint math
-  unsigned masks = 0u;
-  if (WALLS)
-    masks = wall_mask_at(C, 0, r.T.p.x, r.T.p.y) | (wall_mask_at(C, 1, r.A.p.x, r.A.p.y) << 8) |
-            (wall_mask_at(C, 2, r.B.p.x, r.B.p.y) << 16);
+  mT = mA = mB = 0u;
+  if (WALLS && C.n_walls > 0) {
+    mT = wall_mask_at(C, 0, r.T.p.x, r.T.p.y);
+    mA = wall_mask_at(C, 1, r.A.p.x, r.A.p.y);
+    mB = wall_mask_at(C, 2, r.B.p.x, r.B.p.y);
+  }
+}
+
+// One physics substep for the lane's three bodies after `advance` (integrators.kinetic) has run.
+// act_h / act_a: hip / ankle actions.
+// All impulses carry the factor h (C.h_k = h*stiffness, ...), so `potential` is a plain add.
+template <bool WALLS>
+__device__ __forceinline__ void substep(Rig& r, const LegK& k, float act_h, float act_a, const DevConst& C, int leg,
+                                        unsigned mT, unsigned mA, unsigned mB, ContactAcc& acc) {
   const Cols cT = rot_cols(r.T), cA = rot_cols(r.A), cB = rot_cols(r.B);
   const V3 dT = k.ux * cT.c0 + k.uy * cT.c1;  // R_T u: every lever arm of the leg is a scalar times dT / dA / dB
   const V3 dA = k.ux * cA.c0 + k.uy * cA.c1;
@@ -368,7 +380,7 @@ __device__ __forceinline__ void substep(Rig& r, const LegK& k, float act_h, floa
   r.A.w = fma3(C.ang_damp, r.A.w, dwA);
   r.B.w = fma3(C.ang_damp, r.B.w, dwB);
   // ---- colliders on the post-potential state + integrators.collision; impulses accumulate into Info.contact
-  contacts<WALLS>(r, C, dA, dB, masks, leg, acc);
+  contacts<WALLS>(r, C, dA, dB, mT, mA, mB, leg, acc);
 }
 
 // ---- packed state load / store (layout in dev_const.h) -------------------------------------------

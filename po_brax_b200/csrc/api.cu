@@ -26,7 +26,8 @@ cudaError_t launch_fma_probe(float* out, int blocks, int iters, cudaStream_t st)
 struct Handle {
   DevConst C;
   int device;
-  uint8_t* sdf = nullptr;  // wall candidate mask table
+  uint8_t* sdf = nullptr;  // wall candidate mask tables
+  float4* walls = nullptr;
   float2* grid = nullptr;
 };
 }  // namespace pobrax
@@ -209,7 +210,8 @@ static std::vector<float2> gather_grid(const PobraxParams* p) {
   return g;
 }
 
-static int build_dev_const(const PobraxParams* p, DevConst* Cp, std::vector<uint8_t>* sdf, std::vector<float2>* grid) {
+static int build_dev_const(const PobraxParams* p, DevConst* Cp, std::vector<uint8_t>* sdf, std::vector<float2>* grid,
+                           std::vector<float4>* walls) {
   DevConst& C = *Cp;
   std::memset(&C, 0, sizeof(C));
   PobraxLayout L;
@@ -288,13 +290,14 @@ static int build_dev_const(const PobraxParams* p, DevConst* Cp, std::vector<uint
   C.n_walls = (p->env_kind == POBRAX_ANT) ? 0 : p->num_walls;
   C.arena_z = p->arena_z;
   float wlo[pobrax::kMaxWalls][3], whi[pobrax::kMaxWalls][3];
+  walls->clear();
   for (int w = 0; w < C.n_walls; ++w) {
     for (int c = 0; c < 3; ++c) {
       if (!(p->wall_lo[w][c] <= p->wall_hi[w][c])) return fail("wall box with lo > hi");
       wlo[w][c] = p->wall_lo[w][c]; whi[w][c] = p->wall_hi[w][c];
     }
-    C.wall_box[w][0] = make_float4(wlo[w][0], wlo[w][1], wlo[w][2], 0.f);
-    C.wall_box[w][1] = make_float4(whi[w][0], whi[w][1], whi[w][2], 0.f);
+    walls->push_back(make_float4(wlo[w][0], wlo[w][1], wlo[w][2], 0.f));
+    walls->push_back(make_float4(whi[w][0], whi[w][1], whi[w][2], 0.f));
   }
   sdf->clear();
   if (C.n_walls > 0) {
@@ -366,7 +369,8 @@ extern "C" int pobrax_create(const PobraxParams* p, int device, void** handle) {
   DevConst C;
   std::vector<uint8_t> sdf;
   std::vector<float2> grid;
-  if (int rc = build_dev_const(p, &C, &sdf, &grid)) return rc;
+  std::vector<float4> walls;
+  if (int rc = build_dev_const(p, &C, &sdf, &grid, &walls)) return rc;
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess) return fail_cuda("pobrax_create: no CUDA device (this library has no CPU path)", e);
@@ -387,7 +391,12 @@ extern "C" int pobrax_create(const PobraxParams* p, int device, void** handle) {
     if ((e = cudaMalloc(&h->grid, grid.size() * sizeof(float2))) != cudaSuccess) { cudaFree(h->sdf); delete h; cudaSetDevice(prev); return fail_cuda("cudaMalloc(grid)", e); }
     cudaMemcpy(h->grid, grid.data(), grid.size() * sizeof(float2), cudaMemcpyHostToDevice);
   }
+  if (!walls.empty()) {
+    if ((e = cudaMalloc(&h->walls, walls.size() * sizeof(float4))) != cudaSuccess) { cudaFree(h->sdf); cudaFree(h->grid); delete h; cudaSetDevice(prev); return fail_cuda("cudaMalloc(walls)", e); }
+    cudaMemcpy(h->walls, walls.data(), walls.size() * sizeof(float4), cudaMemcpyHostToDevice);
+  }
   C.wall_mask = h->sdf;
+  C.walls = h->walls;
   h->C = C;
   cudaSetDevice(prev);
   *handle = h;
@@ -401,6 +410,7 @@ extern "C" int pobrax_destroy(void* handle) {
   cudaGetDevice(&prev);
   cudaSetDevice(h->device);
   if (h->sdf) cudaFree(h->sdf);
+  if (h->walls) cudaFree(h->walls);
   if (h->grid) cudaFree(h->grid);
   cudaSetDevice(prev);
   delete h;

@@ -187,12 +187,15 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
   acc.Bv = acc.Bw = mk(0.f, 0.f, 0.f);
   acc.cv = row + ObsCols<KIND>::cv;
   acc.ca = acc.cv + 3 * C.nb;
-  if (KIND != POBRAX_ANT && C.n_walls > 0) {
+  {
+    constexpr bool W = KIND != POBRAX_ANT;
+    unsigned mT, mA, mB;
+    advance<W>(r, C, mT, mA, mB);
 #pragma unroll 1
-    for (int s = 0; s < C.substeps; ++s) substep<true>(r, k, act.x, act.y, C, leg, acc);
-  } else {
-#pragma unroll 1
-    for (int s = 0; s < C.substeps; ++s) substep<false>(r, k, act.x, act.y, C, leg, acc);
+    for (int s = C.substeps; s > 0; --s) {
+      substep<W>(r, k, act.x, act.y, C, leg, mT, mA, mB, acc);
+      if (s > 1) advance<W>(r, C, mT, mA, mB);  // rotated loop: kinetic + mask loads of the next substep
+    }
   }
 
   __syncwarp();
@@ -530,13 +533,13 @@ reset_kernel(const __grid_constant__ DevConst C, const PobraxState S, const uint
     const Cols cA = rot_cols(r.A), cB = rot_cols(r.B);
     const V3 dA = k.ux * cA.c0 + k.uy * cA.c1, dB = k.ux * cB.c0 + k.uy * cB.c1;
     Rig tmp = r;
+    unsigned mT = 0u, mA = 0u, mB = 0u;
     if (KIND != POBRAX_ANT && C.n_walls > 0) {
-      const unsigned masks = wall_mask_at(C, 0, r.T.p.x, r.T.p.y) | (wall_mask_at(C, 1, r.A.p.x, r.A.p.y) << 8) |
-                             (wall_mask_at(C, 2, r.B.p.x, r.B.p.y) << 16);
-      contacts<true>(tmp, C, dA, dB, masks, leg, ct);
-    } else {
-      contacts<false>(tmp, C, dA, dB, 0u, leg, ct);
+      mT = wall_mask_at(C, 0, r.T.p.x, r.T.p.y);
+      mA = wall_mask_at(C, 1, r.A.p.x, r.A.p.y);
+      mB = wall_mask_at(C, 2, r.B.p.x, r.B.p.y);
     }
+    contacts<KIND != POBRAX_ANT>(tmp, C, dA, dB, mT, mA, mB, leg, ct);
   }
   __syncwarp();
   stage_common_obs<KIND>(row, r, k, ct, leg, C);

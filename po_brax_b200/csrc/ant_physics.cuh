@@ -84,7 +84,7 @@ __device__ __forceinline__ float limit_and_actuator(float sin_psi, float cos_psi
 // Joint angle and velocity for the observation (Revolute.angle_vel): psi as above, vel = (w_p - w_c).axis_p
 __device__ __forceinline__ void joint_angle_vel(const Body& P, const Body& Cb, V3 axis_p, V3 ref_p, V3 ref_c,
                                                 float& psi, float& vel) {
-  psi = atan2f(dot(cross(ref_p, ref_c), axis_p), dot(ref_p, ref_c));
+  psi = atan2_fast(dot(cross(ref_p, ref_c), axis_p), dot(ref_p, ref_c));
   vel = dot(P.w - Cb.w, axis_p);
 }
 
@@ -240,8 +240,8 @@ __device__ __forceinline__ V3 quad_sum(V3 a) { return mk(quad_sum(a.x), quad_sum
 // stays small enough for the instruction cache:
 //  m != 0: the Arena group -- capsule (segment p + e .. p - e, radius rad) vs its candidate boxes (bit mask m,
 //          boxes in global memory). Contacts are summed and divided by (1e-8 + #contacts with a non-zero dv).
-//          A box whose closest point to the capsule centre is further than sqrt(reach2) (half segment +
-//          radius) cannot touch: skipped exactly.
+//          A box separated from the segment's bounding box by >= rad along some axis cannot touch: skipped
+//          exactly.
 //  m == 0: the torso's ground-plane candidate (sphere vs z = 0).
 __device__ __noinline__ Imp rare_group(V3 p, V3 e, V3 v, V3 w, float rad, float reach2, float inv_m, unsigned m,
                                        const float4* __restrict__ walls, float baumgarte, float friction,
@@ -251,13 +251,18 @@ __device__ __noinline__ Imp rare_group(V3 p, V3 e, V3 v, V3 w, float rad, float 
   Imp o;
   o.dv = o.dw = zero;
   o.hit = 0.0f;
+  const V3 a = p + e, b = p - e;
+  const V3 smin = mk(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z));
+  const V3 smax = mk(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z));
   do {
     const int k = __ffs(m) - 1;
     m &= m - 1;
     const float4 l4 = __ldg(walls + 2 * k), h4 = __ldg(walls + 2 * k + 1);
     const V3 lo = mk(l4.x, l4.y, l4.z), hi = mk(h4.x, h4.y, h4.z);
-    const V3 cd = p - clamp3(p, lo, hi);
-    if (dot(cd, cd) <= reach2) {
+    // exact cull: the distance between the segment and the box is at least their gap along every axis
+    const float gap = fmaxf(fmaxf(fmaxf(lo.x - smax.x, smin.x - hi.x), fmaxf(lo.y - smax.y, smin.y - hi.y)),
+                            fmaxf(lo.z - smax.z, smin.z - hi.z));
+    if (gap < rad) {
       const Imp c = contact_general(p, e, v, w, rad, inv_m, lo, hi, 0, baumgarte, friction, elasticity);
       o.dv += c.dv; o.dw += c.dw; o.hit += c.hit;
     }
@@ -285,7 +290,7 @@ __device__ __forceinline__ void contacts(Rig& r, const DevConst& C, V3 dA, V3 dB
   V3 gv, gw;
   foot_ground(r.B, C.s_foot * dB, C.r_leg, C.inv_m_leg, C, gv, gw);
   const bool hitT = C.r_torso - r.T.p.z > 0.0f;
-  if (hitT || (WALLS && (mT | mA | mB) != 0u)) {  // the one divergent region of the substep (rare)
+  if (__builtin_expect(hitT || (WALLS && (mT | mA | mB) != 0u), 0)) {  // the one divergent region of the substep (rare)
     const V3 zero = mk(0.f, 0.f, 0.f);
     if (hitT || mT != 0u) {
       Imp t;

@@ -106,21 +106,27 @@ __device__ __forceinline__ void gather_readings(float* readings, const Body& T, 
   const float oy = aw * (-y) - ax * (-z) + ay * s + az * (-x);
   const float ori = atan2f(oy, ox);
   const int n_obj = C.n_apples + C.n_bombs, n_read = 2 * C.n_bins;
-  for (int turn = 0; turn < 4; ++turn) {
+  int bins[4];
+  float inten[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {  // all four lanes of the env in parallel
+    const int kobj = 4 * leg + i;
+    bins[i] = n_read;  // "no write"
+    inten[i] = 0.0f;
+    if (kobj < n_obj) {
+      const float ang = __fsub_rn(atan2f(obj[i][0], obj[i][1]), ori);
+      const bool valid = (fabsf(ang) <= C.half_span) && (dist[i] <= C.sensor_range);
+      int bin = valid ? (int)__fdiv_rn(__fadd_rn(ang, C.half_span), C.bin_res) : -1;
+      if (kobj >= C.n_apples && bin >= 0) bin += C.n_apples;
+      inten[i] = bin >= 0 ? __fsub_rn(1.0f, __fdiv_rn(dist[i], C.sensor_range)) : 0.0f;
+      bins[i] = bin < 0 ? bin + n_read : bin;  // index -1 wraps to the last reading
+    }
+  }
+  for (int turn = 0; turn < 4; ++turn) {  // ordered scatter: object 0 first, object n-1 last
     if (turn == leg) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int kobj = 4 * leg + i;
-        if (kobj < n_obj) {
-          const float ang = __fsub_rn(atan2f(obj[i][0], obj[i][1]), ori);
-          const bool valid = (fabsf(ang) <= C.half_span) && (dist[i] <= C.sensor_range);
-          int bin = valid ? (int)__fdiv_rn(__fadd_rn(ang, C.half_span), C.bin_res) : -1;
-          if (kobj >= C.n_apples && bin >= 0) bin += C.n_apples;
-          const float inten = bin >= 0 ? __fsub_rn(1.0f, __fdiv_rn(dist[i], C.sensor_range)) : 0.0f;
-          if (bin < 0) bin += n_read;  // index -1 wraps to the last reading
-          if (bin < n_read) readings[bin] = inten;
-        }
-      }
+      for (int i = 0; i < 4; ++i)
+        if (bins[i] < n_read) readings[bins[i]] = inten[i];
     }
     __syncwarp();
   }
@@ -140,17 +146,21 @@ __device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, const fl
     const int n4 = (rows * D) >> 2;
     const float4* s4 = reinterpret_cast<const float4*>(stage);
     float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll 1
     for (int i = lane; i < n4; i += 32) d4[i] = s4[i];
+#pragma unroll 1
     for (int i = 4 * n4 + lane; i < rows * D; i += 32) dst[i] = stage[i];
   } else {
     for (int es = 0; es < rows; ++es)
       if (!((skip_mask >> es) & 1u))
+#pragma unroll 1
         for (int c = lane; c < D; c += 32) dst[es * D + c] = stage[es * D + c];
   }
   if (first_mask != 0u) {
     __syncwarp();
     for (int es = 0; es < rows; ++es)
       if ((first_mask >> es) & 1u)
+#pragma unroll 1
         for (int c = lane; c < D; c += 32) dst[es * D + c] = first_obs[(env0 + es) * D + c];
   }
 }
@@ -171,6 +181,7 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
   float* stage = smem + (size_t)warp * 8 * D;
   float* row = stage + es * D;
 
+#pragma unroll 1
   for (int i = lane; i < 8 * D; i += 32) stage[i] = 0.0f;
   __syncwarp();
 
@@ -183,18 +194,31 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
   if (C.auto_reset == POBRAX_AUTORESET_CACHED && done_prev != 0.0f) steps = 0.0f;  // AutoResetWrapper.step head
   const float x_before = r.T.p.x;
 
+  // Tag: the opponent's move choice depends only on info['rng'] (ant_tag.py:131-132), not on the physics:
+  // drawn here, while the state loads are still in flight, instead of serialised behind the substep loop.
+  int tag_choice = 0;
+  Key tag_knext; tag_knext.k0 = tag_knext.k1 = 0u;
+  if (KIND == POBRAX_ANT_TAG) {
+    Key key; key.k0 = S.rng[2 * e]; key.k1 = S.rng[2 * e + 1];
+    Key k1;
+    split2(key, tag_knext, k1);
+    tag_choice = randint4(k1);
+  }
   ContactAcc acc;
   acc.Bv = acc.Bw = mk(0.f, 0.f, 0.f);
   acc.cv = row + ObsCols<KIND>::cv;
   acc.ca = acc.cv + 3 * C.nb;
   {
+    // Rotated substep loop, one code copy of each half (the kernel must fit the instruction cache):
+    // iteration s runs the dynamics of substep s-1 and then the kinetic update + wall-mask loads of substep s,
+    // so the three table loads are in flight during the next iteration's joint math.
     constexpr bool W = KIND != POBRAX_ANT;
-    unsigned mT, mA, mB;
-    advance<W>(r, C, mT, mA, mB);
+    unsigned mT = 0u, mA = 0u, mB = 0u;
+    const int nsub = C.substeps;
 #pragma unroll 1
-    for (int s = C.substeps; s > 0; --s) {
-      substep<W>(r, k, act.x, act.y, C, leg, mT, mA, mB, acc);
-      if (s > 1) advance<W>(r, C, mT, mA, mB);  // rotated loop: kinetic + mask loads of the next substep
+    for (int s = 0; s <= nsub; ++s) {
+      if (s > 0) substep<W>(r, k, act.x, act.y, C, leg, mT, mA, mB, acc);
+      if (s < nsub) advance<W>(r, C, mT, mA, mB);
     }
   }
 
@@ -235,10 +259,8 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
     if (leg == 0) row[extra] = in_priest ? (hx > 0.0f ? 1.0f : (hx < 0.0f ? -1.0f : 0.0f)) : 0.0f;
   } else if (KIND == POBRAX_ANT_TAG) {
     // _step_target (ant_tag.py:129-146): rng, rng1 = split(rng); choice = randint(rng1, (), 0, 4)
-    Key key; key.k0 = S.rng[2 * e]; key.k1 = S.rng[2 * e + 1];
-    Key knext, k1;
-    split2(key, knext, k1);
-    const int choice = randint4(k1);
+    const int choice = tag_choice;
+    const Key knext = tag_knext;
     const float tx = S.aux[2 * n + e], ty = S.aux[3 * n + e];
     float vx = __fsub_rn(r.T.p.x, tx), vy = __fsub_rn(r.T.p.y, ty);
     const float nv = norm2_rn(vx, vy);
@@ -416,6 +438,7 @@ reset_kernel(const __grid_constant__ DevConst C, const PobraxState S, const uint
   float* row = stage + es * D;
   uint32_t* sort_keys = reinterpret_cast<uint32_t*>(smem + (size_t)(kThreads / 32) * 8 * D) +
                         (size_t)(warp * 8 + es) * (KIND == POBRAX_ANT_GATHER ? C.n_grid : 0);
+#pragma unroll 1
   for (int i = lane; i < 8 * D; i += 32) stage[i] = 0.0f;
   __syncwarp();
 

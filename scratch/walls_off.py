@@ -1,0 +1,18 @@
+import sys, time, torch
+sys.path.insert(0,'.')
+from po_brax_b200 import envs
+from po_brax_b200.parallel import shard_keys
+n=1<<20
+for name,kw in (('ant_tag',{}),('ant_tag',{'walls':False}),('ant_heavenhell',{}),('ant_heavenhell',{'walls':False}),('ant_gather',{}),('ant_gather',{'walls':False}),('ant',{})):
+    env=envs.create(name,batch_size=n,**kw)
+    s=env.reset(shard_keys(env,0,n,0,1))
+    g=torch.Generator(device='cuda').manual_seed(1)
+    a=torch.rand((4,n,8),device='cuda',generator=g)*2-1
+    for i in range(10): s=env.step(s,a[i%4])
+    torch.cuda.synchronize()
+    e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(40): s=env.step(s,a[i%4])
+    e1.record(); e1.synchronize()
+    print(name,kw,'ms/step',e0.elapsed_time(e1)/40)
+    del env,s

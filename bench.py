@@ -304,7 +304,7 @@ def main_graft(args):
     }
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        m, st_ = 64, 12
+        m, st_ = 64, 200
         v, dt = run_cpu_oracle(args.env, st_, 2, m, 1)
         cpu_baseline = {'value': v, 'unit': 'env-steps/s', 'cores': 1, 'kind': 'port',
                         'sample': f'1 process x {m} envs x {st_} steps of {args.env} (restated NumPy oracle), {dt:.1f} s'}

@@ -1,0 +1,122 @@
+"""Gym-style adapters mirroring /root/reference/po_brax/envs/wrappers.py:126-262 on top of the fused env.
+
+gym itself is not a dependency: the spaces are exposed as plain (low, high, shape) records. Observations,
+rewards and dones are torch CUDA tensors (the reference returns device arrays as well)."""
+from collections import namedtuple
+from typing import Optional
+
+import torch
+
+from .. import random as prandom
+from .env import Env
+
+Box = namedtuple('Box', ['low', 'high', 'shape', 'dtype'])
+
+
+class VmapGymWrapper:
+    """wrappers.py:126-172: batched env behind the gym VectorEnv API; keys = split(key, num_envs + 1)."""
+
+    def __init__(self, env: Env, batch_size: int, seed: int = 0, backend: Optional[str] = None):
+        if batch_size != env.batch_size:
+            raise ValueError('batch_size must equal env.batch_size')
+        self._env = env
+        self.metadata = {'render.modes': ['human', 'rgb_array'],
+                         'video.frames_per_second': 1 / (env.params.dt * env.params.action_repeat)}
+        self.num_envs = batch_size
+        self.seed(seed)
+        self.backend = backend
+        self._state = None
+        inf = float('inf')
+        self.single_observation_space = Box(-inf, inf, (env.observation_size,), 'float32')
+        self.observation_space = Box(-inf, inf, (batch_size, env.observation_size), 'float32')
+        self.single_action_space = Box(-1.0, 1.0, (env.action_size,), 'float32')
+        self.action_space = Box(-1.0, 1.0, (batch_size, env.action_size), 'float32')
+
+    def seed(self, seed: int = 0):
+        self._key = prandom.prng_key(seed)
+
+    def _reset_keys(self):
+        """keys = split(self._key, N + 1): keys[0] is the next gym key (host), keys[1:] the env keys (device)."""
+        n = self.num_envs
+        keys = self._env.split_keys(self._key, n + 1, first=1, count=n)
+        nxt = prandom.split_at(self._key, n + 1, 0)
+        return nxt, keys
+
+    def reset(self):
+        self._key, keys = self._reset_keys()
+        self._state = self._env.reset(keys)
+        return self._state.obs
+
+    def step(self, action):
+        self._state = self._env.step(self._state, action)
+        s = self._state
+        return s.obs, s.reward, s.done, s.metrics
+
+    @property
+    def unwrapped(self):
+        return self._env
+
+
+class AutoresetVmapGymWrapper(VmapGymWrapper):
+    """wrappers.py:240-262: when any env is done, draw a fresh batch of keys from the stored gym key and
+    reset exactly the done envs (qp/obs replaced, steps zeroed; reward/done/metrics/rng/truncation kept).
+    `sync_free=True` skips the reference's `done.any()` host round trip: keys are then drawn every step."""
+
+    def __init__(self, env: Env, batch_size: int, seed: int = 0, backend: Optional[str] = None, sync_free: bool = False):
+        super().__init__(env, batch_size, seed, backend)
+        self.sync_free = sync_free
+
+    def step(self, action):
+        self._state = self._env.step(self._state, action)
+        s = self._state
+        if self.sync_free or bool(s.done.any()):
+            self._key, keys = self._reset_keys()
+            self._state = s = self._env.reset_where_done(s, keys)
+        return s.obs, s.reward, s.done, s.metrics
+
+
+class EvalGymWrapper:
+    """wrappers.py:175-229: running episode statistics (returns, discounted returns, lengths). The reference
+    appends finished episodes to Python lists and reports their nanmean; here the same means are kept as
+    device-side sums and counts, so step() needs no host synchronisation."""
+
+    def __init__(self, env, discount: float = 1.):
+        self.env = env
+        self._discount = discount
+        self.num_envs = getattr(env, 'num_envs', 1)
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    def reset(self, **kwargs):
+        o = self.env.reset(**kwargs)
+        z = torch.zeros(self.num_envs, dtype=torch.float32, device=o.device)
+        self.episode_returns, self.discounted_episode_returns = z.clone(), z.clone()
+        self.episode_lengths = torch.zeros(self.num_envs, dtype=torch.int64, device=o.device)
+        self.current_discount = torch.ones_like(z)
+        self._sums = torch.zeros(4, dtype=torch.float64, device=o.device)  # count, sum r, sum disc r, sum len
+        return o
+
+    def step(self, action):
+        o, r, d, info = self.env.step(action)
+        self.episode_returns += r
+        self.episode_lengths += 1
+        self.discounted_episode_returns += r * self.current_discount
+        self.current_discount *= self._discount
+        dm = d != 0
+        dd = dm.to(torch.float64)
+        self._sums += torch.stack([dd.sum(), (self.episode_returns.double() * dd).sum(),
+                                   (self.discounted_episode_returns.double() * dd).sum(),
+                                   (self.episode_lengths.double() * dd).sum()])
+        self.episode_returns = torch.where(dm, torch.zeros_like(self.episode_returns), self.episode_returns)
+        self.discounted_episode_returns = torch.where(dm, torch.zeros_like(r), self.discounted_episode_returns)
+        self.episode_lengths = torch.where(dm, torch.zeros_like(self.episode_lengths), self.episode_lengths)
+        self.current_discount = torch.where(dm, torch.ones_like(r), self.current_discount)
+        return o, r, d, info
+
+    def get_stats(self):
+        c, sr, sd, sl = self._sums.tolist()
+        nan = float('nan')
+        return {'charts/mean_episodic_return': sr / c if c else nan,
+                'charts/mean_discounted_episodic_return': sd / c if c else nan,
+                'charts/mean_episodic_length': sl / c if c else nan}

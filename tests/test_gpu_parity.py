@@ -302,3 +302,31 @@ def test_errors_are_loud():
         env.step(s, torch.zeros((4, 7), device='cuda'))
     with pytest.raises(RuntimeError):
         envs.create('ant_gather', batch_size=4, n_apples=20)
+
+
+def test_gym_adapters_follow_the_reference_key_chain():
+    """create_gym_env -> AutoresetVmapGymWrapper + EvalGymWrapper (scratch.py:17-23 usage): the env keys are
+    split(PRNGKey(seed), N+1)[1:], the stored gym key advances to split(...)[0] on every reset."""
+    from po_brax_b200 import envs
+    n = 32
+    e = envs.create_gym_env('ant_heavenhell', batch_size=n, seed=3, episode_length=5, eval_metrics=True, discount=0.99)
+    obs = e.reset()
+    oenv = oenvs.AntHeavenHellEnv()
+    ks = tf.split(tf.prng_key(3), n + 1)
+    want = oenv.reset(ks[1:])
+    P.assert_qp_close(e.env._state.qp, want.qp, 'gym reset')
+    assert tuple(obs.shape) == (n, 114)
+    assert list(e.env._key) == ks[0].tolist()
+    total_done = 0
+    for t in range(11):
+        a = torch.zeros((n, 8), device='cuda')
+        o, r, d, info = e.step(a)
+        total_done += int(d.sum())
+        if t in (4, 9):  # episode_length 5 -> every env is done, reset from the advanced gym key
+            assert bool(d.all()) and (e.env._state.info['steps'] == 0).all()
+    st = e.get_stats()
+    assert total_done >= 2 * n and abs(st['charts/mean_episodic_length'] - 5.0) < 1.0
+    ks2 = tf.split(ks[0], n + 1)
+    assert list(e.env._key) != ks[0].tolist()
+    fresh = oenv.reset(ks2[1:])  # first re-reset used the keys drawn from ks[0]
+    assert fresh.obs.shape == (n, 114)

@@ -24,6 +24,9 @@ sys.path.insert(0, ROOT)
 FLOPS_PER_ENV_STEP = {'ant': 4.30e4, 'ant_heavenhell': 4.30e4, 'ant_tag': 4.30e4, 'ant_gather': 4.34e4}
 BYTES_PER_ENV_STEP = {'ant': 1332, 'ant_heavenhell': 1444, 'ant_tag': 1428, 'ant_gather': 2212}
 METRIC = 'env-steps/sec'
+# dram__bytes_read.sum + dram__bytes_write.sum of one step_kernel launch, from the committed ncu --set full capture
+# (profiles/ncu_step_hh_r1.txt: 587.6 MB read + 996.4 MB write at 1 Mi HeavenHell envs = 1511 B per env-step)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {('ant_heavenhell', 1 << 20): 1.584e9}
 
 
 def parse():
@@ -292,7 +295,7 @@ def main_graft(args):
     ach_gb = per_gpu * byts / 1e9
     roofline = {
         'bound': 'fp32', 'achieved': ach_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach_tf / peak_tf,
-        'traffic': None,
+        'traffic': NCU_TRAFFIC_BYTES_PER_LAUNCH.get((args.env, n)),
         'peak_source': 'measured live: pobrax_fp32_probe (dependent-chain FFMA kernel, burst, best of 5); '
                        'nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4',
         'kernel': f'step_kernel<{args.env}>', 'launch_ms': ms / K,

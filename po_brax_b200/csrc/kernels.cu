@@ -181,16 +181,22 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
   float* stage = smem + (size_t)warp * 8 * D;
   float* row = stage + es * D;
 
-#pragma unroll 1
-  for (int i = lane; i < 8 * D; i += 32) stage[i] = 0.0f;
-  __syncwarp();
-
+  // Issue every global load of the step first (state planes, action, episode scalars, task aux), then zero the
+  // staging rows while they are in flight. The memory clobber / register pins keep the compiler from sinking the
+  // loads down to their first use behind the substep loop.
   const LegK k = leg_consts(C, leg);
   Rig r;
   load_rig(reinterpret_cast<const float4*>(S.qp), n, e, leg, r);
   const float2 act = reinterpret_cast<const float2*>(action)[e * 4 + leg];
   float steps = S.steps[e];
-  const float done_prev = S.done[e];
+  float done_prev = S.done[e];
+  float ep_ret = C.track_metrics ? S.ep_return[e] : 0.0f;
+  float aux_side = (KIND == POBRAX_ANT_HEAVENHELL) ? S.aux[2 * n + e] : 0.0f;
+  asm volatile("" ::: "memory");
+#pragma unroll 1
+  for (int i = lane; i < 8 * D; i += 32) stage[i] = 0.0f;
+  __syncwarp();
+  asm volatile("" : "+f"(steps), "+f"(done_prev), "+f"(ep_ret), "+f"(aux_side));
   if (C.auto_reset == POBRAX_AUTORESET_CACHED && done_prev != 0.0f) steps = 0.0f;  // AutoResetWrapper.step head
   const float x_before = r.T.p.x;
 
@@ -244,7 +250,7 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
     done = dead;
     m0 = ctrl; m1 = contact; m2 = forward; m3 = 1.0f;
   } else if (KIND == POBRAX_ANT_HEAVENHELL) {
-    const int side = S.aux[2 * n + e] != 0.0f ? 1 : 0;
+    const int side = aux_side != 0.0f ? 1 : 0;
     const float hx = C.hh_xy[side][0], hy = C.hh_xy[side][1];
     const float lx = C.hh_xy[1 - side][0], ly = C.hh_xy[1 - side][1];
     const bool in_heaven = norm2_rn(hx - r.T.p.x, hy - r.T.p.y) <= C.visible_radius;
@@ -352,7 +358,7 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
     if (C.metrics_dim > 2) S.metrics[2 * n + e] = m2;
     if (C.metrics_dim > 3) S.metrics[3 * n + e] = m3;
     if (C.track_metrics) {
-      const float ret = S.ep_return[e] + reward;
+      const float ret = ep_ret + reward;
       S.ep_return[e] = done != 0.0f ? 0.0f : ret;
       if (done != 0.0f) {
         atomicAdd(S.acc + 0, 1.0);

@@ -167,7 +167,7 @@ __device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, const fl
 
 // --------------------------------------------------------------------------------------------- step
 template <int KIND>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, KIND == POBRAX_ANT ? 5 : 4)
 step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float* __restrict__ action) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

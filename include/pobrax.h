@@ -144,6 +144,10 @@ int pobrax_pack_qp(void* handle, const float* pos, const float* rot, const float
 /* jax.random.split(key, n): key = host uint32[2]; out = device uint32[n][2] (rows first..first+count). */
 int pobrax_split_keys(const uint32_t key[2], int n, int first, int count, uint32_t* out, void* stream);
 
+/* vmapped jax.random.split(key, 2) on device keys uint32[n][2]: out_a = split[0], out_b = split[1]
+ * (the `rng, rng1 = jp.random_split(state.info['rng'], 2)` of envs/wrappers.py:102). */
+int pobrax_split_pairs(const uint32_t* keys, int n, uint32_t* out_a, uint32_t* out_b, void* stream);
+
 /* Measurement aid (bench.py): one launch of `blocks` x 256 threads x `iters` x 64 dependent-chain FMAs;
  * *flops = FLOPs of the launch (FMA = 2). out: device float[blocks * 256] scratch. */
 int pobrax_fp32_probe(float* out, int blocks, int iters, void* stream, double* flops);

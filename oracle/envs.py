@@ -366,3 +366,27 @@ def gym_reset_keys(key, num_envs):
     """VmapGymWrapper._reset (wrappers.py:160-163): keys = split(key, N+1); (next gym key, env keys)."""
     ks = tf.split(np.asarray(key, np.uint32), num_envs + 1)
     return ks[0], ks[1:]
+
+
+class RandomizedAutoResetNaive:
+    """wrappers.py:30-52 (and :55-80, identical results) on top of Episode(env) without AutoReset:
+    steps <- 0 where done; done <- 0; inner step; qp/obs <- reset(state.info['rng']) where done."""
+
+    def __init__(self, env, episode_length=1000):
+        self.inner = EpisodeAutoReset(env, episode_length, auto_reset=False)
+        self.env = env
+
+    def reset(self, rng):
+        return self.inner.reset(rng)
+
+    def step(self, state, action):
+        info = dict(state.info)
+        info['steps'] = np.where(np.asarray(state.done, F) > 0, F(0), info['steps']).astype(F)
+        state = state.replace(done=np.zeros_like(np.asarray(state.done, F)), info=info)
+        s = self.inner.step(state, action)
+        fresh = self.inner.reset(s.info['rng'])
+        d = np.asarray(s.done, bool)
+        qp = bx.QP(*[np.where(d.reshape((-1,) + (1,) * (x.ndim - 1)), x, y) for x, y in
+                     ((fresh.qp.pos, s.qp.pos), (fresh.qp.rot, s.qp.rot), (fresh.qp.vel, s.qp.vel),
+                      (fresh.qp.ang, s.qp.ang))])
+        return s.replace(qp=qp, obs=np.where(d[:, None], fresh.obs, s.obs))

@@ -64,6 +64,7 @@ EXPORTS = {
     'pobrax_reset_where_done': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PobraxState), C.c_void_p]),
     'pobrax_unpack_qp': (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),
     'pobrax_pack_qp': (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),
+    'pobrax_split_pairs': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'pobrax_fp32_probe': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]),
     'pobrax_split_keys': (C.c_int, [C.POINTER(C.c_uint32), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }

@@ -22,6 +22,7 @@ cudaError_t launch_pack(const DevConst& C, const float* pos, const float* rot, c
                         float* qp, float* aux, cudaStream_t st);
 cudaError_t launch_split_keys(const uint32_t key[2], int n, int first, int count, uint32_t* out, cudaStream_t st);
 cudaError_t launch_fma_probe(float* out, int blocks, int iters, cudaStream_t st);
+cudaError_t launch_split_pairs(const uint32_t* keys, int n, uint32_t* a, uint32_t* b, cudaStream_t st);
 
 struct Handle {
   DevConst C;
@@ -495,4 +496,10 @@ extern "C" int pobrax_fp32_probe(float* out, int blocks, int iters, void* stream
   cudaError_t e = pobrax::launch_fma_probe(out, blocks, iters, static_cast<cudaStream_t>(stream));
   if (flops) *flops = (double)blocks * 256.0 * (double)iters * 64.0 * 2.0;
   return e == cudaSuccess ? 0 : fail_cuda("pobrax_fp32_probe launch", e);
+}
+
+extern "C" int pobrax_split_pairs(const uint32_t* keys, int n, uint32_t* out_a, uint32_t* out_b, void* stream) {
+  if (!keys || !out_a || !out_b || n < 0) return fail("pobrax_split_pairs: bad argument");
+  cudaError_t e = pobrax::launch_split_pairs(keys, n, out_a, out_b, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? 0 : fail_cuda("pobrax_split_pairs launch", e);
 }

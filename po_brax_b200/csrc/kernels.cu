@@ -720,6 +720,18 @@ __global__ void split_keys_kernel(Key key, int n, int first, int count, uint32_t
   out[2 * i + 1] = k.k1;
 }
 
+// vmapped jax.random.split(key, 2): keys[n][2] -> a[n][2] (split[0]), b[n][2] (split[1])
+__global__ void split_pairs_kernel(const uint32_t* __restrict__ keys, int n, uint32_t* __restrict__ a,
+                                   uint32_t* __restrict__ b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Key k; k.k0 = keys[2 * i]; k.k1 = keys[2 * i + 1];
+  Key ka, kb;
+  split2(k, ka, kb);
+  a[2 * i] = ka.k0; a[2 * i + 1] = ka.k1;
+  b[2 * i] = kb.k0; b[2 * i + 1] = kb.k1;
+}
+
 // ------------------------------------------------------------------------------------------ launchers
 static size_t obs_stage_bytes(const DevConst& C) { return (size_t)(kThreads / 32) * 8 * C.obs_dim * sizeof(float); }
 
@@ -783,6 +795,12 @@ cudaError_t launch_pack(const DevConst& C, const float* pos, const float* rot, c
                         float* qp, float* aux, cudaStream_t st) {
   const size_t total = (size_t)C.n_envs * C.nb;
   pack_qp_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(C, pos, rot, vel, ang, qp, aux);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_split_pairs(const uint32_t* keys, int n, uint32_t* a, uint32_t* b, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  split_pairs_kernel<<<(n + 255) / 256, 256, 0, st>>>(keys, n, a, b);
   return cudaGetLastError();
 }
 

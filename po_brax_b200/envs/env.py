@@ -333,6 +333,15 @@ class Env:
                        'pobrax_split_keys')
         return out
 
+    def split_pairs(self, keys: torch.Tensor):
+        """vmapped jax.random.split(keys, 2) -> (keys[:, 0], keys[:, 1]) for device keys [N, 2]."""
+        keys = keys.contiguous()
+        a, b = torch.empty_like(keys), torch.empty_like(keys)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pobrax_split_pairs(keys.data_ptr(), keys.shape[0], a.data_ptr(), b.data_ptr(),
+                                                   self._stream()), 'pobrax_split_pairs')
+        return a, b
+
     # ---- helpers for State
     def _unpack(self, qp, aux) -> QP:
         n, nb = self.batch_size, self.num_bodies

@@ -13,6 +13,81 @@ from .env import Env
 Box = namedtuple('Box', ['low', 'high', 'shape', 'dtype'])
 
 
+class _FunctionalWrapper:
+    """brax.envs.env.Wrapper surface: forwards everything to the wrapped env."""
+
+    def __init__(self, env: Env):
+        self.env = env
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    def reset(self, rng):
+        return self.env.reset(rng)
+
+    @property
+    def unwrapped(self):
+        return self.env.unwrapped
+
+
+def _episode_head(state):
+    """The head shared by the autoreset wrappers (wrappers.py:36-40): steps <- 0 where done; done <- 0."""
+    b = state.buf
+    b['steps'].mul_(1.0 - b['done'])
+    b['done'].zero_()
+
+
+class RandomizedAutoResetWrapperNaive(_FunctionalWrapper):
+    """wrappers.py:30-52: where done, qp/obs <- a fresh `reset(state.info['rng'])` (only qp and obs are taken, so
+    HeavenHell / Gather, whose info['rng'] never changes, re-reset to the identical state; Tag's key advances every
+    step). Wrap an env built with auto_reset=False. Envs without info['rng'] (plain ant) raise KeyError, as in the
+    reference."""
+
+    def step(self, state, action):
+        if self.env.auto_reset:
+            raise RuntimeError('wrap an env created with auto_reset=False')
+        if state.buf['rng'] is None:
+            raise KeyError('rng')
+        _episode_head(state)
+        state = self.env.step(state, action)
+        steps = state.buf['steps'].clone()  # the select leaves info['steps'] alone (it is zeroed at the next head)
+        state = self.env.reset_where_done(state, state.buf['rng'])
+        state.buf['steps'].copy_(steps)
+        return state
+
+
+class RandomizedAutoResetWrapperOnTerminal(RandomizedAutoResetWrapperNaive):
+    """wrappers.py:55-80: same result as Naive; the reference merely skips the reset computation when no env is
+    done (lax.cond). The fused reset kernel already only computes the done envs."""
+
+
+class RandomizedAutoResetWrapperCached(_FunctionalWrapper):
+    """wrappers.py:83-123: brax-style cached autoreset whose cached first state is refreshed every
+    `n_steps_between_updates` calls from `reset(split(info['rng'])[1])`, info['rng'] <- split(...)[0].
+    Wrap an env built with auto_reset=True (the cached select runs inside the step kernel)."""
+
+    def __init__(self, env: Env, n_steps_between_updates: int = 200):
+        super().__init__(env)
+        self.n_steps_between_updates = n_steps_between_updates
+        self.steps = 0
+
+    def step(self, state, action):
+        if not self.env.auto_reset:
+            raise RuntimeError('wrap an env created with auto_reset=True')
+        self.steps += 1
+        if (self.steps % self.n_steps_between_updates) == 0:
+            if state.buf['rng'] is None:
+                raise KeyError('rng')
+            rng, rng1 = self.env.split_pairs(state.buf['rng'])
+            s = self.env.reset(rng1)
+            state.buf['first_qp'].copy_(s.buf['qp'])
+            if state.buf['first_aux'] is not None:
+                state.buf['first_aux'].copy_(s.buf['aux'])
+            state.buf['first_obs'].copy_(s.buf['obs'])
+            state.buf['rng'].copy_(rng)
+        return self.env.step(state, action)
+
+
 class VmapGymWrapper:
     """wrappers.py:126-172: batched env behind the gym VectorEnv API; keys = split(key, num_envs + 1)."""
 

@@ -330,3 +330,110 @@ def test_gym_adapters_follow_the_reference_key_chain():
     assert list(e.env._key) != ks[0].tolist()
     fresh = oenv.reset(ks2[1:])  # first re-reset used the keys drawn from ks[0]
     assert fresh.obs.shape == (n, 114)
+
+
+@pytest.mark.parametrize('kind', ['ant_heavenhell', 'ant_tag'])
+def test_randomized_autoreset_naive(kind):
+    """wrappers.py:30-80: where done, qp/obs <- reset(info['rng']); Tag's key advances each step, HeavenHell's
+    never does (every re-reset is the same state)."""
+    from po_brax_b200 import envs
+    from po_brax_b200.envs.wrappers import RandomizedAutoResetWrapperNaive
+    n, L, T = 48, 3, 8
+    keys = P.keys_for(n, seed=21)
+    o = oenvs.RandomizedAutoResetNaive(oenvs.ENVS[kind](), episode_length=L)
+    s = o.reset(keys)
+    w = RandomizedAutoResetWrapperNaive(envs.create(kind, batch_size=n, episode_length=L, auto_reset=False))
+    cs = w.reset(keys)
+    rng = tf.prng_key(4)
+    for t in range(T):
+        rng, a = P.actions_for(rng, n)
+        s = o.step(s, a)
+        cs = w.step(cs, torch.as_tensor(a, device='cuda'))
+        assert np.array_equal(P.t2n(cs.info['steps']), s.info['steps']), t
+        assert np.array_equal(P.t2n(cs.done), np.asarray(s.done, np.float32)), t
+        assert (P.rng_bits(cs.info['rng']) == s.info['rng']).all()
+        P.assert_qp_close(cs.qp, s.qp, f'{kind} randomized autoreset t={t}', vel_atol=5e-3, pos_scale=10.0)
+        if (t + 1) % L == 0:  # every env just hit the episode limit: qp is a fresh reset, bit-exact frozen bodies
+            assert np.array_equal(P.t2n(cs.qp.pos)[:, 10:], s.qp.pos[:, 10:])
+
+
+def test_randomized_autoreset_cached_refreshes_first_state():
+    from po_brax_b200 import envs
+    from po_brax_b200.envs.wrappers import RandomizedAutoResetWrapperCached
+    n = 32
+    keys = P.keys_for(n, seed=22)
+    w = RandomizedAutoResetWrapperCached(envs.create('ant_tag', batch_size=n, episode_length=1000), n_steps_between_updates=3)
+    cs = w.reset(keys)
+    first0 = cs.buf['first_qp'].clone()
+    a = torch.zeros((n, 8), device='cuda')
+    cs = w.step(cs, a); cs = w.step(cs, a)
+    assert torch.equal(cs.buf['first_qp'], first0)
+    rng_before = P.rng_bits(cs.info['rng']).copy()
+    cs = w.step(cs, a)  # 3rd call: refresh from reset(split(rng)[1]); rng <- split(rng)[0], then the step advances it
+    assert not torch.equal(cs.buf['first_qp'], first0)
+    want_rng = tf.split(tf.split(rng_before, 2)[:, 0], 2)[:, 0]
+    assert (P.rng_bits(cs.info['rng']) == want_rng).all()
+    fresh = oenvs.AntTagEnv().reset(tf.split(rng_before, 2)[:, 1])
+    P.assert_qp_close(w.env._unpack(cs.buf['first_qp'], cs.buf['first_aux']), fresh.qp, 'refreshed first_qp')
+
+
+def test_action_repeat_scales_dt_and_substeps():
+    """ActionRepeatWrapper (wrappers.py:16-24): dt *= k, substeps *= k, i.e. 20 substeps of the same h."""
+    n = 32
+    keys = P.keys_for(n, seed=23)
+    oenv = oenvs.AntHeavenHellEnv(action_repeat=2)
+    assert oenv.sys.substeps == 20
+    s = oenv.reset(keys)
+    env = _make('ant_heavenhell', n, action_repeat=2, auto_reset=False)
+    cs = env.reset(keys)
+    rng = tf.prng_key(9)
+    oenv.sys.track_margin = True
+    dirty = np.zeros(n, bool)
+    for t in range(3):
+        rng, a = P.actions_for(rng, n)
+        oenv.sys.margin = None
+        s = oenv.step(s, a)
+        cs = env.step(cs, torch.as_tensor(a, device='cuda'))
+        dirty |= oenv.sys.margin <= P.BRANCH_MARGIN
+        P.assert_qp_close(cs.qp, s.qp, f'action_repeat t={t}', vel_atol=5e-3, pos_scale=10.0, rows=~dirty)
+    assert (~dirty).mean() > 0.25  # 60 substeps: many envs pass through a rounding-ambiguous branch
+
+
+@pytest.mark.parametrize('kind,n', [('ant', 4096), ('ant_gather', 16384), ('ant_tag', 65536)])
+def test_baseline_configs_invariants(kind, n):
+    """BASELINE configs 2-4 at their full sizes with autoreset: size-independent properties over a 120-step
+    rollout with a short episode limit (so every env resets several times)."""
+    from po_brax_b200 import standard_observability_masks as M
+    env = _make(kind, n, episode_length=25, auto_reset=True, eval_metrics=True)
+    keys = env.split_keys((0, 77), n + 1, first=1, count=n)
+    s = env.reset(keys)
+    first_obs = s.info['first_obs'].clone()
+    g = torch.Generator(device='cuda').manual_seed(3)
+    done_total = 0
+    for t in range(120):
+        a = torch.rand((n, 8), device='cuda', generator=g) * 2 - 1
+        s = env.step(s, a)
+        d = s.done.bool()
+        done_total += int(d.sum())
+        assert torch.equal(s.obs[d], first_obs[d])                 # cached autoreset: obs <- first_obs where done
+        assert (s.info['steps'] <= 25).all() and ((s.done == 0) | (s.done == 1)).all()
+    q = s.qp
+    assert torch.isfinite(s.obs).all() and torch.isfinite(q.pos).all() and torch.isfinite(q.vel).all()
+    assert (q.rot[:, :9].norm(dim=-1) - 1).abs().max() < 1e-5    # unit quaternions
+    assert torch.equal(q.vel[:, 9:], torch.zeros_like(q.vel[:, 9:]))  # frozen bodies never move by physics
+    acc = dict(zip(env.ACC_NAMES, s.buf['acc'].tolist()))
+    assert acc['episodes'] == done_total >= 4 * n and acc['sum_length'] <= 25 * acc['episodes']
+    if kind == 'ant':   # standard_observability_masks: the three 'ant' index sets partition the 87 columns
+        o = s.obs
+        parts = [M.apply_mask(o, M.POSITION['ant']), M.apply_mask(o, M.VELOCITY['ant']), M.apply_mask(o, M.CFRC['ant'])]
+        assert [p.shape[1] for p in parts] == [13, 14, 60] and torch.equal(torch.cat(parts, 1), o)
+        assert (parts[2].abs() <= 1).all()                          # contact columns are clipped to [-1, 1]
+    if kind == 'ant_gather':
+        obj = q.pos[:, 11:]
+        on_grid = (obj[..., :2] == obj[..., :2].round()).all(-1) & (obj[..., :2].abs() <= 6).all(-1)
+        waiting = (obj == torch.tensor([18., 18., 12.], device='cuda')).all(-1)
+        assert (on_grid | waiting).all()                             # objects sit on the integer grid or wait at (18,18,12)
+        assert (s.obs[:, -20:] >= 0).all() and (s.obs[:, -20:] <= 1).all()
+    if kind == 'ant_tag':
+        tgt = q.pos[:, 10]
+        assert (tgt[:, :2].abs() <= 4.5 + 1e-6).all()               # the opponent never leaves its cage

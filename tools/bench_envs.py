@@ -1,5 +1,8 @@
+"""Per-env step time (1 Mi envs, 40 timed steps after 10 warm-up steps), walls on / off (test hook):
+    python tools/bench_envs.py
+"""
 import sys, time, torch
-sys.path.insert(0,'.')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from po_brax_b200 import envs
 from po_brax_b200.parallel import shard_keys
 n=1<<20

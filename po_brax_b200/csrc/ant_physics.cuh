@@ -279,6 +279,38 @@ __device__ __forceinline__ Imp wall_group(const Body& b, V3 e, float rad, float 
   return rare_group(b.p, e, b.v, b.w, rad, reach * reach, inv_m, m, C.walls, C.baumgarte, C.friction, C.elasticity);
 }
 
+// Inline fast path of a body's Arena group for the common case -- ONE candidate box and the closest segment point
+// at an end (g(0) >= 0 or g(1) <= 0 in seg_box_t, i.e. no bisection): same arithmetic as contact_general, but
+// from the constant bank and without the call. Returns false when the out-of-line group has to run instead.
+__device__ __forceinline__ bool wall_single(const Body& b, V3 e, float rad, float inv_m, unsigned m, const DevConst& C,
+                                            Imp& c) {
+  if (m & (m - 1u)) return false;
+  const int k = __ffs(m) - 1;
+  const float4 l4 = C.wall_box[k][0], h4 = C.wall_box[k][1];
+  const V3 lo = mk(l4.x, l4.y, l4.z), hi = mk(h4.x, h4.y, h4.z);
+  const V3 a = b.p + e;
+  const V3 d = (b.p - e) - a;
+  const V3 p1 = a + d;  // g(1) is evaluated at a + 1*d, as in seg_box_t
+  const V3 ca = clamp3(a, lo, hi), cb = clamp3(p1, lo, hi);
+  const V3 da = a - ca, db = p1 - cb;
+  const bool t0 = dot(da, d) >= 0.0f;
+  if (!t0 && !(dot(db, d) <= 0.0f)) return false;  // interior minimum: bisection, out of line
+  const V3 dvec = t0 ? da : db, bp = t0 ? ca : cb;
+  c.dv = c.dw = mk(0.f, 0.f, 0.f);
+  c.hit = 0.0f;
+  const float d2 = dot(dvec, dvec), rs = rad + 1e-6f;
+  if (d2 < rs * rs) {
+    const float dist = sqrtf(d2);
+    const float pen = rad - dist;
+    if (pen > 0.0f) {
+      const V3 n = (1.0f / (1e-6f + dist)) * dvec;
+      const V3 rel = bp - b.p;
+      c = impulse(rel, b.v + cross(b.w, rel), n, pen, inv_m, C.baumgarte, C.friction, C.elasticity);
+    }
+  }
+  return true;
+}
+
 // Σ colliders.apply(qp) for the lane's bodies -- ground (torso sphere, foot end) + Arena walls (all three) --
 // evaluated on the state in `r`; then integrators.collision (vel += dv, ang += dw) and the Info.contact sums.
 // Every contact is evaluated on the same (pre-collision) state: a body's impulses are applied only after all
@@ -299,19 +331,25 @@ __device__ __forceinline__ void contacts(Rig& r, const DevConst& C, V3 dA, V3 dB
         t = rare_group(r.T.p, zero, r.T.v, r.T.w, C.r_torso, 0.0f, C.inv_m_torso, 0u, C.walls, C.baumgarte, C.friction,
                        C.elasticity);
       if (WALLS && mT != 0u) {
-        const Imp c = wall_group(r.T, zero, C.r_torso, C.r_torso + 1e-4f, C.inv_m_torso, mT, C);
+        Imp c;
+        if (!wall_single(r.T, zero, C.r_torso, C.inv_m_torso, mT, C, c))
+          c = wall_group(r.T, zero, C.r_torso, C.r_torso + 1e-4f, C.inv_m_torso, mT, C);
         t.dv += c.dv; t.dw += c.dw;
       }
       r.T.v += t.dv; r.T.w += t.dw;
       if (leg == 0) { row_add(acc.cv, 0, t.dv); row_add(acc.ca, 0, t.dw); }
     }
     if (WALLS && mA != 0u) {
-      const Imp c = wall_group(r.A, C.s_aux * dA, C.r_leg, C.seg_aux + C.r_leg + 1e-4f, C.inv_m_leg, mA, C);
+      Imp c;
+      if (!wall_single(r.A, C.s_aux * dA, C.r_leg, C.inv_m_leg, mA, C, c))
+        c = wall_group(r.A, C.s_aux * dA, C.r_leg, C.seg_aux + C.r_leg + 1e-4f, C.inv_m_leg, mA, C);
       r.A.v += c.dv; r.A.w += c.dw;
       row_add(acc.cv, 1 + 2 * leg, c.dv); row_add(acc.ca, 1 + 2 * leg, c.dw);
     }
     if (WALLS && mB != 0u) {
-      const Imp c = wall_group(r.B, C.s_foot * dB, C.r_leg, C.seg_foot + C.r_leg + 1e-4f, C.inv_m_leg, mB, C);
+      Imp c;
+      if (!wall_single(r.B, C.s_foot * dB, C.r_leg, C.inv_m_leg, mB, C, c))
+        c = wall_group(r.B, C.s_foot * dB, C.r_leg, C.seg_foot + C.r_leg + 1e-4f, C.inv_m_leg, mB, C);
       r.B.v += c.dv; r.B.w += c.dw;
       acc.Bv += c.dv; acc.Bw += c.dw;
     }

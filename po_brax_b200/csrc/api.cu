@@ -298,6 +298,8 @@ static int build_dev_const(const PobraxParams* p, DevConst* Cp, std::vector<uint
       wlo[w][c] = p->wall_lo[w][c]; whi[w][c] = p->wall_hi[w][c];
     }
     walls->push_back(make_float4(wlo[w][0], wlo[w][1], wlo[w][2], 0.f));
+    C.wall_box[w][0] = make_float4(wlo[w][0], wlo[w][1], wlo[w][2], 0.f);
+    C.wall_box[w][1] = make_float4(whi[w][0], whi[w][1], whi[w][2], 0.f);
     walls->push_back(make_float4(whi[w][0], whi[w][1], whi[w][2], 0.f));
   }
   sdf->clear();

@@ -50,6 +50,7 @@ struct DevConst {
   float hip_default, ank_default[4];         // default_angle(): limit midpoints
   // walls: axis-aligned boxes in world coordinates + a per-cell candidate mask for exact culling
   const float4* walls;                       // device float4[n_walls][2]: (lo.xyz, -), (hi.xyz, -)
+  float4 wall_box[kMaxWalls][2];             // the same boxes in the constant bank (inline fast path)
   const uint8_t* wall_mask;                  // [3 body types][sdf_ny][sdf_nx] candidate-wall bit mask of each xy cell
   int32_t sdf_plane;                         // sdf_nx * sdf_ny
   float sdf_x0, sdf_y0, sdf_inv_cell;

@@ -23,6 +23,13 @@ constexpr int kEnvsPerBlock = kThreads / 4;
 
 // ------------------------------------------------------------------------------------------- helpers
 __device__ __forceinline__ float clip1(float x) { return fminf(fmaxf(x, -1.0f), 1.0f); }
+// A global load issued exactly here (volatile asm): the compilers otherwise sink the step's small scalar loads
+// down to their first use behind the substep loop, where their DRAM latency is exposed.
+__device__ __forceinline__ float ld_now(const float* p) {
+  float v;
+  asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 // jp.norm of a 2-vector without FMA contraction (keeps <= radius tests identical to the CPU oracle's)
 __device__ __forceinline__ float norm2_rn(float dx, float dy) {
   return sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
@@ -188,15 +195,18 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
   Rig r;
   load_rig(reinterpret_cast<const float4*>(S.qp), n, e, leg, r);
   const float2 act = reinterpret_cast<const float2*>(action)[e * 4 + leg];
-  float steps = S.steps[e];
-  float done_prev = S.done[e];
-  float ep_ret = C.track_metrics ? S.ep_return[e] : 0.0f;
-  float aux_side = (KIND == POBRAX_ANT_HEAVENHELL) ? S.aux[2 * n + e] : 0.0f;
+  float steps = ld_now(S.steps + e);
+  float done_prev = ld_now(S.done + e);
+  float ep_ret = C.track_metrics ? ld_now(S.ep_return + e) : 0.0f;
+  float aux_side = (KIND == POBRAX_ANT_HEAVENHELL) ? ld_now(S.aux + 2 * n + e) : 0.0f;
   asm volatile("" ::: "memory");
+  {
+    float4* s4 = reinterpret_cast<float4*>(stage);  // 8 rows = 32*D bytes: a whole number of float4
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-  for (int i = lane; i < 8 * D; i += 32) stage[i] = 0.0f;
+    for (int i = lane; i < 2 * D; i += 32) s4[i] = z;
+  }
   __syncwarp();
-  asm volatile("" : "+f"(steps), "+f"(done_prev), "+f"(ep_ret), "+f"(aux_side));
   if (C.auto_reset == POBRAX_AUTORESET_CACHED && done_prev != 0.0f) steps = 0.0f;  // AutoResetWrapper.step head
   const float x_before = r.T.p.x;
 

@@ -198,10 +198,11 @@ __device__ __forceinline__ Imp contact_general(V3 p, V3 e, V3 v, V3 w, float rad
 // reach of the table cell (exact rectangle-rectangle distance in xy, so culling stays exact). One table per
 // body type `kind` (0 torso sphere, 1 Aux capsule, 2 lower-leg capsule); outside the table: every wall.
 __device__ __forceinline__ unsigned wall_mask_at(const DevConst& C, int kind, float x, float y) {
-  const float fx = (x - C.sdf_x0) * C.sdf_inv_cell, fy = (y - C.sdf_y0) * C.sdf_inv_cell;
-  const int ix = min(max((int)fx, 0), C.sdf_nx - 1);
-  const int iy = min(max((int)fy, 0), C.sdf_ny - 1);
-  return __ldg(C.wall_mask + kind * C.sdf_plane + iy * C.sdf_nx + ix);
+  // cell = (p - origin) / cell_size, one FMA per axis; the unsigned min sends negatives (and NaN -> 0) to a border
+  // cell, and border cells list every wall.
+  const unsigned ix = min((unsigned)(int)fmaf(x, C.sdf_inv_cell, C.sdf_bx), (unsigned)(C.sdf_nx - 1));
+  const unsigned iy = min((unsigned)(int)fmaf(y, C.sdf_inv_cell, C.sdf_by), (unsigned)(C.sdf_ny - 1));
+  return __ldg(C.wall_mask + (unsigned)(kind * C.sdf_plane) + iy * (unsigned)C.sdf_nx + ix);
 }
 
 // Per-lane constants of leg l.

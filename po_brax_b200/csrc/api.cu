@@ -334,6 +334,7 @@ static int build_dev_const(const PobraxParams* p, DevConst* Cp, std::vector<uint
           (*sdf)[k * plane + (size_t)iy * nx + ix] = m;
         }
     C.sdf_x0 = (float)x0; C.sdf_y0 = (float)y0; C.sdf_inv_cell = (float)(1.0 / cell);
+    C.sdf_bx = (float)(-x0 / cell); C.sdf_by = (float)(-y0 / cell);
     C.sdf_nx = nx; C.sdf_ny = ny; C.sdf_plane = (int)plane;
   }
   // ---- task

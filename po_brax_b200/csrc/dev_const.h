@@ -53,7 +53,7 @@ struct DevConst {
   float4 wall_box[kMaxWalls][2];             // the same boxes in the constant bank (inline fast path)
   const uint8_t* wall_mask;                  // [3 body types][sdf_ny][sdf_nx] candidate-wall bit mask of each xy cell
   int32_t sdf_plane;                         // sdf_nx * sdf_ny
-  float sdf_x0, sdf_y0, sdf_inv_cell;
+  float sdf_x0, sdf_y0, sdf_inv_cell, sdf_bx, sdf_by;   // sdf_bx = -x0 * inv_cell (cell = fma(p, inv_cell, b))
   int32_t sdf_nx, sdf_ny;
   // task
   float dying_cost, visible_radius;

@@ -43,8 +43,7 @@ __device__ __forceinline__ void kinetic(Body& b, float h) {
   const float y = b.qy - ax * b.qz + ay * b.qw + az * b.qx;
   const float z = b.qz + ax * b.qy - ay * b.qx + az * b.qw;
   const float n2 = w * w + x * x + y * y + z * z;
-  float r = rsqrtf(n2);
-  r = r * fmaf(-0.5f * n2, r * r, 1.5f);  // one Newton step: ~0.5 ulp reciprocal norm
+  const float r = rsqrtf(n2);  // <= 2 ulp; the norm error does not accumulate (renormalised every substep)
   b.qw = w * r; b.qx = x * r; b.qy = y * r; b.qz = z * r;
 }
 
@@ -131,7 +130,8 @@ __device__ __forceinline__ void foot_ground(const Body& b, V3 e, float r, float 
   const float J = (C.baumgarte * pen - (1.0f + C.elasticity) * nv) * rden;
   const bool apply_n = (pen > 0.0f) && (nv < 0.0f) && (J > 0.0f);
   const float Jn = apply_n ? J : 0.0f;
-  const float nd = sqrtf(vx * vx + vy * vy);
+  const float s2 = vx * vx + vy * vy;
+  const float nd = s2 > 0.0f ? s2 * rsqrtf(s2) : 0.0f;  // |v_d| to ~2 ulp (feeds a min() and a 0.01 threshold)
   const float cd = __fdividef(-fminf(nd * rden, C.friction * J), 1e-6f + nd);
   const float c = (apply_n && nd > 0.01f) ? cd : 0.0f;
   const float jx = c * vx, jy = c * vy;

@@ -50,6 +50,8 @@ typedef struct PobraxParams {
   int32_t auto_reset;       /* PobraxAutoReset */
   int32_t action_repeat;    /* wrappers.py:16-24: dt *= k, substeps *= k (applied at create) */
   int32_t track_metrics;    /* 1: maintain ep_return + acc[] (device-side episode statistics) */
+  int32_t obs_col_lo, obs_col_hi; /* emit only observation columns [lo, hi) (0, 0 = all): the contiguous index sets of
+                                     standard_observability_masks.py ('ant': 0:13, 13:27, 27:87) fused into the store */
   /* ---- brax system (Ant) ---- */
   float dt;                 /* 0.05 */
   int32_t substeps;         /* 10 */
@@ -106,7 +108,7 @@ typedef struct PobraxState {
 
 typedef struct PobraxLayout {
   int32_t num_bodies;   /* nb of the brax system: Ant 10, Tag 12, HeavenHell 14, Gather 27 */
-  int32_t obs_dim;      /* 87 / 103 / 114 / 211 */
+  int32_t obs_dim;      /* 87 / 103 / 114 / 211, or obs_col_hi - obs_col_lo when a column range is selected */
   int32_t aux_dim;
   int32_t metrics_dim;
   int32_t action_dim;   /* 8 */

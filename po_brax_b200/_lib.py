@@ -17,7 +17,7 @@ _f, _i = C.c_float, C.c_int32
 class PobraxParams(C.Structure):
     _fields_ = [
         ('env_kind', _i), ('num_envs', _i), ('episode_length', _i), ('auto_reset', _i), ('action_repeat', _i),
-        ('track_metrics', _i),
+        ('track_metrics', _i), ('obs_col_lo', _i), ('obs_col_hi', _i),
         ('dt', _f), ('substeps', _i), ('gravity_z', _f), ('velocity_damping', _f), ('angular_damping', _f),
         ('baumgarte_erp', _f), ('friction', _f), ('elasticity', _f),
         ('torso_mass', _f), ('leg_mass', _f), ('torso_radius', _f), ('leg_radius', _f),

@@ -189,6 +189,11 @@ static int layout_of(const PobraxParams* p, PobraxLayout* L) {
       break;
     default: return fail("unknown env_kind");
   }
+  if (p->obs_col_lo != 0 || p->obs_col_hi != 0) {
+    if (p->obs_col_lo < 0 || p->obs_col_hi > L->obs_dim || p->obs_col_lo >= p->obs_col_hi)
+      return fail("obs_col_lo/obs_col_hi must select a non-empty column range inside the observation");
+    L->obs_dim = p->obs_col_hi - p->obs_col_lo;
+  }
   L->action_dim = 8;
   L->qp_planes = POBRAX_QP_PLANES;
   return 0;
@@ -222,7 +227,16 @@ static int build_dev_const(const PobraxParams* p, DevConst* Cp, std::vector<uint
   if (p->substeps < 1 || !(p->dt > 0.0f)) return fail("dt and substeps must be positive");
   if (p->num_walls < 0 || p->num_walls > POBRAX_MAX_WALLS) return fail("num_walls out of range");
   if (p->auto_reset != POBRAX_AUTORESET_OFF && p->auto_reset != POBRAX_AUTORESET_CACHED) return fail("unknown auto_reset mode");
-  C.n_envs = p->num_envs; C.env_kind = p->env_kind; C.nb = L.num_bodies; C.obs_dim = L.obs_dim;
+  C.n_envs = p->num_envs; C.env_kind = p->env_kind; C.nb = L.num_bodies;
+  {  // full observation width (staging) vs the emitted column range
+    PobraxParams full = *p;
+    full.obs_col_lo = full.obs_col_hi = 0;
+    PobraxLayout Lf;
+    if (int rc = layout_of(&full, &Lf)) return rc;
+    C.obs_dim = Lf.obs_dim;
+    C.obs_lo = (p->obs_col_lo == 0 && p->obs_col_hi == 0) ? 0 : p->obs_col_lo;
+    C.obs_out = L.obs_dim;
+  }
   C.aux_dim = L.aux_dim; C.metrics_dim = L.metrics_dim;
   C.episode_length = p->episode_length; C.auto_reset = p->auto_reset; C.track_metrics = p->track_metrics;
   C.has_rng = p->env_kind != POBRAX_ANT;

@@ -144,12 +144,13 @@ __device__ __forceinline__ void gather_readings(float* readings, const Body& T, 
 // 16-byte boundary because env0 is a multiple of 8). Rows in `first_mask` are then overwritten from the cached
 // first_obs (rare), rows in `skip_mask` are left untouched (reset_where_done).
 __device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, const float* __restrict__ first_obs,
-                                               const float* stage, int D, long long env0, int n_envs, unsigned first_mask,
-                                               unsigned skip_mask, int lane) {
+                                               const float* stage, int D, int lo, int Do, long long env0, int n_envs,
+                                               unsigned first_mask, unsigned skip_mask, int lane) {
+  // D: staged row width, [lo, lo + Do): emitted columns (Do == D: the whole row, contiguous float4 path)
   const int rows = (int)min((long long)8, (long long)n_envs - env0);
   if (rows <= 0) return;
-  float* dst = obs + env0 * D;
-  if (skip_mask == 0u) {
+  float* dst = obs + env0 * Do;
+  if (skip_mask == 0u && Do == D) {
     const int n4 = (rows * D) >> 2;
     const float4* s4 = reinterpret_cast<const float4*>(stage);
     float4* d4 = reinterpret_cast<float4*>(dst);
@@ -161,14 +162,14 @@ __device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, const fl
     for (int es = 0; es < rows; ++es)
       if (!((skip_mask >> es) & 1u))
 #pragma unroll 1
-        for (int c = lane; c < D; c += 32) dst[es * D + c] = stage[es * D + c];
+        for (int c = lane; c < Do; c += 32) dst[es * Do + c] = stage[es * D + lo + c];
   }
   if (first_mask != 0u) {
     __syncwarp();
     for (int es = 0; es < rows; ++es)
       if ((first_mask >> es) & 1u)
 #pragma unroll 1
-        for (int c = lane; c < D; c += 32) dst[es * D + c] = first_obs[(env0 + es) * D + c];
+        for (int c = lane; c < Do; c += 32) dst[es * Do + c] = first_obs[(env0 + es) * Do + c];
   }
 }
 
@@ -395,7 +396,7 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
   unsigned fm8 = 0;
   for (int i = 0; i < 8; ++i) fm8 |= ((first_mask >> (4 * i)) & 1u) << i;
   __syncwarp();
-  write_obs_rows(S.obs, S.first_obs, stage, D, env0, C.n_envs, fm8, 0u, lane);
+  write_obs_rows(S.obs, S.first_obs, stage, D, C.obs_lo, C.obs_out, env0, C.n_envs, fm8, 0u, lane);
 }
 
 // -------------------------------------------------------------------------------------------- reset
@@ -630,8 +631,8 @@ reset_kernel(const __grid_constant__ DevConst C, const PobraxState S, const uint
   unsigned sk8 = 0;
   for (int i = 0; i < 8; ++i) sk8 |= ((skip >> (4 * i)) & 1u) << i;
   __syncwarp();
-  write_obs_rows(S.obs, S.obs, stage, D, env0, C.n_envs, 0u, sk8, lane);
-  if (!only_done && S.first_obs) write_obs_rows(S.first_obs, S.obs, stage, D, env0, C.n_envs, 0u, sk8, lane);
+  write_obs_rows(S.obs, S.obs, stage, D, C.obs_lo, C.obs_out, env0, C.n_envs, 0u, sk8, lane);
+  if (!only_done && S.first_obs) write_obs_rows(S.first_obs, S.obs, stage, D, C.obs_lo, C.obs_out, env0, C.n_envs, 0u, sk8, lane);
 }
 
 // --------------------------------------------------------------------------- brax.QP <-> packed state

@@ -224,6 +224,14 @@ class Env:
             pop2('cage_xy', p.gather_cage_xy)
             _lib.check(self.lib.pobrax_draw_arena(C.byref(p), p.gather_cage_xy[0] + 1.0, p.gather_cage_xy[1] + 1.0,
                                                   0.5), 'pobrax_draw_arena')
+        if 'obs_mask' in kw:  # fused standard_observability_masks subset: a name ('position' | 'velocity' | 'cfrc',
+            m = kw.pop('obs_mask')  # plain ant only) or an explicit (lo, hi) column range
+            if isinstance(m, str):
+                if name != 'ant':
+                    raise ValueError('named observability masks exist for the plain ant only; pass (lo, hi)')
+                m = {'position': (0, 13), 'velocity': (13, 27), 'cfrc': (27, 87)}[m]
+            if m is not None:
+                p.obs_col_lo, p.obs_col_hi = int(m[0]), int(m[1])
         if kw.pop('walls', True) is False:  # test hook: drop the Arena colliders
             p.num_walls = 0
         kw.pop('legacy_spring', None)

@@ -103,3 +103,14 @@ def test_no_gpu_means_loud_failure(lib):
     from po_brax_b200 import envs
     with pytest.raises(RuntimeError):
         envs.create('ant', batch_size=4)
+
+
+def test_observation_column_range(lib):
+    """obs_col_lo/hi (the fused observability masks) change only the reported observation width."""
+    p, L = _lib.PobraxParams(), _lib.PobraxLayout()
+    lib.pobrax_default_params(_lib.ANT, C.byref(p))
+    for lo, hi in ((0, 13), (13, 27), (27, 87)):
+        p.obs_col_lo, p.obs_col_hi = lo, hi
+        assert lib.pobrax_layout(C.byref(p), C.byref(L)) == 0 and L.obs_dim == hi - lo
+    p.obs_col_lo, p.obs_col_hi = 50, 100
+    assert lib.pobrax_layout(C.byref(p), C.byref(L)) != 0

@@ -437,3 +437,41 @@ def test_baseline_configs_invariants(kind, n):
     if kind == 'ant_tag':
         tgt = q.pos[:, 10]
         assert (tgt[:, :2].abs() <= 4.5 + 1e-6).all()               # the opponent never leaves its cage
+
+
+@pytest.mark.parametrize('mask', ['position', 'velocity', 'cfrc'])
+def test_fused_observability_mask(mask):
+    """standard_observability_masks 'ant' rows fused into the store: the masked env emits exactly obs[:, MASK]."""
+    from po_brax_b200 import standard_observability_masks as M
+    n = 200  # not a multiple of 8 or 32: exercises the ragged last warp
+    keys = P.keys_for(n, seed=31)
+    full, part = _make('ant', n, episode_length=4), _make('ant', n, episode_length=4, obs_mask=mask)
+    idx = {'position': M.POSITION, 'velocity': M.VELOCITY, 'cfrc': M.CFRC}[mask]['ant']
+    assert part.observation_size == len(idx)
+    a, b = full.reset(keys), part.reset(keys)
+    assert torch.equal(M.apply_mask(a.obs, idx), b.obs)
+    g = torch.Generator(device='cuda').manual_seed(5)
+    for t in range(9):
+        act = torch.rand((n, 8), device='cuda', generator=g) * 2 - 1
+        a, b = full.step(a, act), part.step(b, act)
+        assert torch.equal(M.apply_mask(a.obs, idx), b.obs), t
+        assert torch.equal(a.buf['qp'], b.buf['qp']) and torch.equal(a.reward, b.reward) and torch.equal(a.done, b.done)
+
+
+def test_ragged_and_tiny_batches():
+    """Batch sizes that do not fill a warp / CTA, and batch_size None (one env)."""
+    for kind in KINDS:
+        for n in (1, 5, 33):
+            keys = P.keys_for(64, seed=41)[:n]
+            big = _make(kind, 64)
+            small = _make(kind, n)
+            sb, ss = big.reset(P.keys_for(64, seed=41)), small.reset(keys)
+            a = torch.zeros((64, 8), device='cuda')
+            a[:, ::2] = 0.3
+            for _ in range(3):
+                sb, ss = big.step(sb, a), small.step(ss, a[:n].contiguous())
+            assert torch.equal(sb.obs[:n], ss.obs) and torch.equal(sb.buf['qp'][:, :n], ss.buf['qp'])
+    from po_brax_b200 import envs
+    one = envs.create('ant_tag')  # batch_size None -> a single env
+    s = one.reset(P.keys_for(1))
+    assert tuple(s.obs.shape) == (1, 103)

@@ -76,6 +76,8 @@ class State:
         info = {'steps': b['steps'], 'truncation': b['truncation']}
         if b['rng'] is not None:
             info['rng'] = b['rng']  # uint32 bit patterns stored as int32 [N, 2]
+        if b['acc'] is not None:  # create(..., eval_metrics=True): device-side episode statistics (brax EvalWrapper's role)
+            info['eval_metrics'] = dict(zip(Env.ACC_NAMES, b['acc'].unbind(0)))
         if b['first_qp'] is not None:
             info['first_obs'] = b['first_obs']
             info['first_qp'] = _LazyQP(self._env, b['first_qp'], b['first_aux'])

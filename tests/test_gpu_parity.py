@@ -475,3 +475,23 @@ def test_ragged_and_tiny_batches():
     one = envs.create('ant_tag')  # batch_size None -> a single env
     s = one.reset(P.keys_for(1))
     assert tuple(s.obs.shape) == (1, 103)
+
+
+def test_eval_metrics_accumulators_match_a_host_recount():
+    """create(..., eval_metrics=True): the device-side accumulators equal what a host loop counts from done / reward."""
+    n, L = 512, 7
+    env = _make('ant_heavenhell', n, episode_length=L, auto_reset=True, eval_metrics=True)
+    s = env.reset(P.keys_for(n, seed=51))
+    g = torch.Generator(device='cuda').manual_seed(7)
+    ret = torch.zeros(n, device='cuda', dtype=torch.float64)
+    episodes = sum_ret = sum_len = trunc = 0.0
+    for t in range(30):
+        s = env.step(s, torch.rand((n, 8), device='cuda', generator=g) * 2 - 1)
+        ret += s.reward.double()
+        d = s.done.bool()
+        episodes += float(d.sum()); sum_ret += float(ret[d].sum()); sum_len += float(s.info['steps'][d].sum())
+        trunc += float(s.info['truncation'].sum())
+        ret[d] = 0
+    em = {k: float(v) for k, v in s.info['eval_metrics'].items()}
+    assert em['episodes'] == episodes and em['sum_length'] == sum_len and em['truncations'] == trunc
+    assert abs(em['sum_return'] - sum_ret) < 1e-6

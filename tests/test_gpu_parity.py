@@ -495,3 +495,41 @@ def test_eval_metrics_accumulators_match_a_host_recount():
     em = {k: float(v) for k, v in s.info['eval_metrics'].items()}
     assert em['episodes'] == episodes and em['sum_length'] == sum_len and em['truncations'] == trunc
     assert abs(em['sum_return'] - sum_ret) < 1e-6
+
+
+@pytest.mark.parametrize('kind,kw', [
+    ('ant_gather', dict(n_apples=3, n_bombs=2, n_bins=6, cage_xy=(4, 5), catch_range=1.5, sensor_range=4.0, dying_cost=-3.0)),
+    ('ant_tag', dict(tag_radius=2.0, visible_radius=6.0, target_step=0.25, min_spawn_distance=3.0, cage_xy=(3.5, 4.0), dying_cost=-0.5)),
+    ('ant_heavenhell', dict(heaven_hell=((-4.0, 6.0), (4.0, 6.0)), priest_position=(0.0, 6.0), visible_radius=2.5, dying_cost=-1.0)),
+])
+def test_constructor_kwargs_of_the_reference_envs(kind, kw):
+    """Non-default constructor arguments (ant_gather.py:59-69, ant_tag.py:38-45, ant_heavenhell.py:51-56) reach the
+    kernels: reset parity + teacher-forced steps against the oracle built with the same arguments."""
+    n, T = 96, 6
+    keys = P.keys_for(n, seed=61)
+    oenv = oenvs.ENVS[kind](**kw)
+    env = _make(kind, n, auto_reset=False, **kw)
+    nb = oenv.sys.num_bodies
+    assert env.observation_size == oenv.reset(keys[:2]).obs.shape[1] and env.num_bodies == nb
+    s = oenv.reset(keys)
+    cs = env.reset(keys)
+    assert np.array_equal(P.t2n(cs.qp.pos)[:, 9:], s.qp.pos[:, 9:])
+    P.assert_qp_close(cs.qp, s.qp, f'{kind} kwargs reset')
+    rng = tf.prng_key(8)
+    oenv.sys.track_margin = True
+    for t in range(T):
+        rng, a = P.actions_for(rng, n)
+        c0 = env.state_from_qp(P.qp_to_torch(s.qp), rng=s.info.get('rng'))
+        oenv.sys.margin = None
+        nxt = oenv.step(oenvs.State(s.qp.copy(), s.obs, s.reward, s.done, dict(s.metrics), dict(s.info)), a)
+        got = env.step(c0, torch.as_tensor(a, device='cuda'))
+        clear = oenv.sys.margin > P.BRANCH_MARGIN
+        P.assert_qp_close(got.qp, nxt.qp, f'{kind} kwargs t={t}', rows=clear)
+        assert np.array_equal(P.t2n(got.done), np.asarray(nxt.done, np.float32))
+        assert np.array_equal(P.t2n(got.reward), nxt.reward)
+        mask = np.ones_like(nxt.obs, bool)
+        mask[~clear] = False
+        if kind == 'ant_gather':
+            mask[:, -2 * oenv.n_bins:] &= _gather_reading_mask(oenv, nxt, got)
+        P.assert_obs_close(P.t2n(got.obs), nxt.obs, kind, nb, f'{kind} kwargs t={t}', mask=mask)
+        s = nxt

@@ -39,11 +39,6 @@ __device__ __forceinline__ float uniform_rn(uint32_t bits, float lo, float hi) {
   const float f = bits_to_unit(bits);
   return fmaxf(lo, __fadd_rn(__fmul_rn(f, __fsub_rn(hi, lo)), lo));
 }
-__device__ __forceinline__ int quad_or(int x) {
-  x |= __shfl_xor_sync(kFull, x, 1);
-  x |= __shfl_xor_sync(kFull, x, 2);
-  return x;
-}
 __device__ __forceinline__ int quad_and(int x) {
   x &= __shfl_xor_sync(kFull, x, 1);
   x &= __shfl_xor_sync(kFull, x, 2);

@@ -10,7 +10,7 @@ torch's current stream. The env is always batched (the reference's VmapWrapper a
 stack ActionRepeat -> Episode -> Vmap -> AutoReset of `create()` is fused into the step kernel.
 """
 import ctypes as C
-from typing import Dict, Optional, Sequence
+from typing import Dict, Optional
 
 import numpy as np
 import torch

@@ -106,7 +106,7 @@ __device__ __forceinline__ void gather_readings(float* readings, const Body& T, 
   const float aw = -x, ax = s, ay = z, az = -y;
   const float ox = aw * (-x) + ax * s + ay * (-z) - az * (-y);
   const float oy = aw * (-y) - ax * (-z) + ay * s + az * (-x);
-  const float ori = atan2f(oy, ox);
+  const float ori = atan2_fast(oy, ox);
   const int n_obj = C.n_apples + C.n_bombs, n_read = 2 * C.n_bins;
   int bins[4];
   float inten[4];
@@ -116,7 +116,7 @@ __device__ __forceinline__ void gather_readings(float* readings, const Body& T, 
     bins[i] = n_read;  // "no write"
     inten[i] = 0.0f;
     if (kobj < n_obj) {
-      const float ang = __fsub_rn(atan2f(obj[i][0], obj[i][1]), ori);
+      const float ang = __fsub_rn(atan2_fast(obj[i][0], obj[i][1]), ori);
       const bool valid = (fabsf(ang) <= C.half_span) && (dist[i] <= C.sensor_range);
       int bin = valid ? (int)__fdiv_rn(__fadd_rn(ang, C.half_span), C.bin_res) : -1;
       if (kobj >= C.n_apples && bin >= 0) bin += C.n_apples;

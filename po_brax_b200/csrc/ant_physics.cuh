@@ -304,7 +304,7 @@ __device__ __forceinline__ bool wall_single(const Body& b, V3 e, float rad, floa
     const float dist = sqrtf(d2);
     const float pen = rad - dist;
     if (pen > 0.0f) {
-      const V3 n = (1.0f / (1e-6f + dist)) * dvec;
+      const V3 n = __fdividef(1.0f, 1e-6f + dist) * dvec;
       const V3 rel = bp - b.p;
       c = impulse(rel, b.v + cross(b.w, rel), n, pen, inv_m, C.baumgarte, C.friction, C.elasticity);
     }

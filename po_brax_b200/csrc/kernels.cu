@@ -8,7 +8,7 @@
 //   ant_tag.py:63-105, brax.envs.ant.Ant.reset (threefry bit-exact), and with only_done=1 the gym-level
 //   autoreset select of /root/reference/po_brax/envs/wrappers.py:245-262.
 //
-// Thread mapping: 4 lanes = 1 env (lane l owns leg l and a replica of the torso); 128 threads = 32 envs.
+// Thread mapping: 4 lanes = 1 env (lane l owns leg l and a replica of the torso); a warp = 8 envs.
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -18,8 +18,15 @@
 
 namespace pobrax {
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 128;             // reset kernels
 constexpr int kEnvsPerBlock = kThreads / 4;
+// Step kernels use small CTAs (1-2 warps): warps never wait for each other, so finer CTAs let the hardware
+// scheduler balance warps of different cost (wall contacts) and shorten the tail. Measured per env family.
+template <int KIND> struct StepCfg {
+  static constexpr int threads = (KIND == POBRAX_ANT || KIND == POBRAX_ANT_TAG) ? 32 : 64;
+  static constexpr int envs = threads / 4;
+  static constexpr int min_blocks = (KIND == POBRAX_ANT ? 5 : 4) * (128 / threads);   // 96 / 128 registers
+};
 
 // ------------------------------------------------------------------------------------------- helpers
 __device__ __forceinline__ float clip1(float x) { return fminf(fmaxf(x, -1.0f), 1.0f); }
@@ -170,14 +177,14 @@ __device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, const fl
 
 // --------------------------------------------------------------------------------------------- step
 template <int KIND>
-__global__ void __launch_bounds__(kThreads, KIND == POBRAX_ANT ? 5 : 4)
+__global__ void __launch_bounds__(StepCfg<KIND>::threads, StepCfg<KIND>::min_blocks)
 step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float* __restrict__ action) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int leg = lane & 3, es = lane >> 2;
   const int D = C.obs_dim;
   const size_t n = (size_t)C.n_envs;
-  const long long env0 = ((long long)blockIdx.x * kEnvsPerBlock) + warp * 8;
+  const long long env0 = ((long long)blockIdx.x * StepCfg<KIND>::envs) + warp * 8;
   const long long env_raw = env0 + es;
   const bool valid = env_raw < (long long)n;
   const size_t e = valid ? (size_t)env_raw : n - 1;  // out-of-range lanes shadow the last env (no stores)
@@ -743,14 +750,14 @@ static size_t obs_stage_bytes(const DevConst& C) { return (size_t)(kThreads / 32
 
 template <int KIND>
 static cudaError_t launch_step_t(const DevConst& C, const PobraxState& S, const float* action, cudaStream_t st) {
-  const size_t smem = obs_stage_bytes(C);
+  const size_t smem = (size_t)(StepCfg<KIND>::threads / 32) * 8 * C.obs_dim * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(step_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr_set = true;
   }
-  const int blocks = (C.n_envs + kEnvsPerBlock - 1) / kEnvsPerBlock;
-  step_kernel<KIND><<<blocks, kThreads, smem, st>>>(C, S, action);
+  const int blocks = (C.n_envs + StepCfg<KIND>::envs - 1) / StepCfg<KIND>::envs;
+  step_kernel<KIND><<<blocks, StepCfg<KIND>::threads, smem, st>>>(C, S, action);
   return cudaGetLastError();
 }
 

@@ -289,6 +289,14 @@ __device__ __forceinline__ bool wall_single(const Body& b, V3 e, float rad, floa
   const int k = __ffs(m) - 1;
   const float4 l4 = C.wall_box[k][0], h4 = C.wall_box[k][1];
   const V3 lo = mk(l4.x, l4.y, l4.z), hi = mk(h4.x, h4.y, h4.z);
+  c.dv = c.dw = mk(0.f, 0.f, 0.f);
+  c.hit = 0.0f;
+  {  // exact early-out: the segment's bounding box is separated from the box by > rad along some axis
+    const float ex = fabsf(e.x), ey = fabsf(e.y), ez = fabsf(e.z), rs = rad + 1e-5f;
+    const float gap = fmaxf(fmaxf(fmaxf(lo.x - (b.p.x + ex), (b.p.x - ex) - hi.x), fmaxf(lo.y - (b.p.y + ey), (b.p.y - ey) - hi.y)),
+                            fmaxf(lo.z - (b.p.z + ez), (b.p.z - ez) - hi.z));
+    if (gap > rs) return true;
+  }
   const V3 a = b.p + e;
   const V3 d = (b.p - e) - a;
   const V3 p1 = a + d;  // g(1) is evaluated at a + 1*d, as in seg_box_t
@@ -297,8 +305,6 @@ __device__ __forceinline__ bool wall_single(const Body& b, V3 e, float rad, floa
   const bool t0 = dot(da, d) >= 0.0f;
   if (!t0 && !(dot(db, d) <= 0.0f)) return false;  // interior minimum: bisection, out of line
   const V3 dvec = t0 ? da : db, bp = t0 ? ca : cb;
-  c.dv = c.dw = mk(0.f, 0.f, 0.f);
-  c.hit = 0.0f;
   const float d2 = dot(dvec, dvec), rs = rad + 1e-6f;
   if (d2 < rs * rs) {
     const float dist = sqrtf(d2);

@@ -462,6 +462,7 @@ reset_kernel(const __grid_constant__ DevConst C, const PobraxState S, const uint
   __syncwarp();
 
   const bool active = !only_done || S.done[e] != 0.0f;  // uniform over the quad
+  if (only_done && !__any_sync(kFull, active)) return;   // gym autoreset: most warps have no finished env
   const LegK k = leg_consts(C, leg);
   Key key; key.k0 = keys[2 * e]; key.k1 = keys[2 * e + 1];
   constexpr int NSPLIT = (KIND == POBRAX_ANT) ? 3 : (KIND == POBRAX_ANT_GATHER ? 4 : 5);

@@ -1,0 +1,15 @@
+"""Gym-path timing: AutoresetVmapGymWrapper.step (step kernel + done.any() sync + reset_where_done) per step."""
+import os, sys, time, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from po_brax_b200 import envs
+n = 1 << 20
+for sync_free in (False, True):
+    e = envs.create_gym_env('ant_heavenhell', batch_size=n, seed=0)
+    e.sync_free = sync_free
+    e.reset()
+    a = torch.rand((n, 8), device='cuda') * 2 - 1
+    for _ in range(10): e.step(a)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(50): e.step(a)
+    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 50
+    print('gym step, sync_free', sync_free, 'ms/step', round(dt * 1e3, 3), 'env-steps/s', f'{n / dt:.3e}')

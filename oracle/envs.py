@@ -384,6 +384,7 @@ class RandomizedAutoResetNaive:
         info['steps'] = np.where(np.asarray(state.done, F) > 0, F(0), info['steps']).astype(F)
         state = state.replace(done=np.zeros_like(np.asarray(state.done, F)), info=info)
         s = self.inner.step(state, action)
+        self.step_margin = self.env.sys.margin   # test aid (brax_v1._note_margin): the step's, not the reset's below
         fresh = self.inner.reset(s.info['rng'])
         d = np.asarray(s.done, bool)
         qp = bx.QP(*[np.where(d.reshape((-1,) + (1,) * (x.ndim - 1)), x, y) for x, y in

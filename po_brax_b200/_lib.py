@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libpobrax.so')
+LIB_PATH = os.environ.get('POBRAX_LIB') or os.path.join(HERE, 'libpobrax.so')   # POBRAX_LIB: tuning builds
 
 ABI_VERSION = 1
 ANT, ANT_HEAVENHELL, ANT_GATHER, ANT_TAG = 0, 1, 2, 3

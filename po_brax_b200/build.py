@@ -30,17 +30,18 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    if not force and not is_stale():
+def build(force=False, verbose=False, out=None, extra=()):
+    """out / extra: tuning builds (another output path, extra nvcc flags such as -DPOBRAX_WALL_WARPS_PER_SMSP=5)."""
+    if out is None and not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB] + \
+    cmd = [_nvcc()] + NVCC_FLAGS + list(extra) + (['-Xptxas', '-v'] if verbose else []) + ['-o', out or LIB] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == '__main__':

@@ -87,6 +87,12 @@ __device__ __forceinline__ void joint_angle_vel(const Body& P, const Body& Cb, V
   vel = dot(P.w - Cb.w, axis_p);
 }
 
+// Bare MUFU.RSQ / MUFU.RCP (no denormal-range fix-up code): the arguments here are never denormal -- quaternion
+// norms, 1/m + lever^2, 1e-6 + |v|, max(|sin|, |cos|). sqrt_pos: sqrt to ~2 ulp for lengths (0 below 1e-15).
+__device__ __forceinline__ float rsqrt_ftz(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_ftz(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_pos(float x) { return x > 1e-30f ? x * rsqrt_ftz(x) : 0.0f; }
+
 struct Imp { V3 dv, dw; float hit; };  // one contact's (dvel, dang) and whether it is non-zero
 
 // OneWayCollider contact impulse on a unit-inertia body, general normal.
@@ -98,17 +104,17 @@ __device__ __forceinline__ Imp impulse(V3 rel, V3 v, V3 n, float pen, float inv_
   o.hit = 0.0f;
   const float nv = dot(n, v);
   const V3 t1 = cross(rel, n);
-  const float rden = __fdividef(1.0f, inv_m + dot(n, cross(t1, rel)));
+  const float rden = rcp_ftz(inv_m + dot(n, cross(t1, rel)));
   const float J = (baumgarte * pen - (1.0f + elasticity) * nv) * rden;
   if (!((pen > 0.0f) && (nv < 0.0f) && (J > 0.0f))) return o;
   const V3 Jn = J * n;
   o.dv = inv_m * Jn;
   o.dw = cross(rel, Jn);
   const V3 vd = v - nv * n;
-  const float nd = sqrtf(dot(vd, vd));
+  const float nd = sqrt_pos(dot(vd, vd));
   if (nd > 0.01f) {
     const float Jd = fminf(nd * rden, friction * J);
-    const V3 Jdv = __fdividef(-Jd, 1e-6f + nd) * vd;
+    const V3 Jdv = (-Jd * rcp_ftz(1e-6f + nd)) * vd;
     o.dv += inv_m * Jdv;
     o.dw += cross(rel, Jdv);
   }
@@ -123,16 +129,15 @@ __device__ __forceinline__ void foot_ground(const Body& b, V3 e, float r, float 
                                             V3& dw) {
   const float pen = r - (b.p.z + e.z);
   const float rx = e.x, ry = e.y, rz = e.z - r;
-  const float vx = b.v.x + (b.w.y * rz - b.w.z * ry);
-  const float vy = b.v.y + (b.w.z * rx - b.w.x * rz);
-  const float nv = b.v.z + (b.w.x * ry - b.w.y * rx);
-  const float rden = __fdividef(1.0f, inv_m + (rx * rx + ry * ry));
+  const float vx = fmaf(b.w.y, rz, fmaf(-b.w.z, ry, b.v.x));
+  const float vy = fmaf(b.w.z, rx, fmaf(-b.w.x, rz, b.v.y));
+  const float nv = fmaf(b.w.x, ry, fmaf(-b.w.y, rx, b.v.z));
+  const float rden = rcp_ftz(fmaf(rx, rx, fmaf(ry, ry, inv_m)));
   const float J = (C.baumgarte * pen - (1.0f + C.elasticity) * nv) * rden;
   const bool apply_n = (pen > 0.0f) && (nv < 0.0f) && (J > 0.0f);
   const float Jn = apply_n ? J : 0.0f;
-  const float s2 = vx * vx + vy * vy;
-  const float nd = s2 > 0.0f ? s2 * rsqrtf(s2) : 0.0f;  // |v_d| to ~2 ulp (feeds a min() and a 0.01 threshold)
-  const float cd = __fdividef(-fminf(nd * rden, C.friction * J), 1e-6f + nd);
+  const float nd = sqrt_pos(fmaf(vx, vx, vy * vy));  // |v_d| to ~2 ulp (feeds a min() and a 0.01 threshold)
+  const float cd = -fminf(nd * rden, C.friction * J) * rcp_ftz(1e-6f + nd);
   const float c = (apply_n && nd > 0.01f) ? cd : 0.0f;
   const float jx = c * vx, jy = c * vy;
   dv = mk(inv_m * jx, inv_m * jy, inv_m * Jn);
@@ -236,6 +241,17 @@ __device__ __forceinline__ float quad_sum(float x) {
   return x;
 }
 __device__ __forceinline__ V3 quad_sum(V3 a) { return mk(quad_sum(a.x), quad_sum(a.y), quad_sum(a.z)); }
+// Two V3 at once: 12 shuffles, the adds packed pairwise (same butterfly order: bit-identical in the 4 lanes)
+__device__ __forceinline__ void quad_sum2(V3& a, V3& b) {
+  F2 p0 = pk(a.x, a.y), p1 = pk(a.z, b.x), p2 = pk(b.y, b.z);
+#pragma unroll
+  for (int m = 1; m <= 2; m <<= 1) {
+    p0 = p0 + pk(__shfl_xor_sync(kFull, lo(p0), m), __shfl_xor_sync(kFull, hi(p0), m));
+    p1 = p1 + pk(__shfl_xor_sync(kFull, lo(p1), m), __shfl_xor_sync(kFull, hi(p1), m));
+    p2 = p2 + pk(__shfl_xor_sync(kFull, lo(p2), m), __shfl_xor_sync(kFull, hi(p2), m));
+  }
+  a = mk(lo(p0), hi(p0), lo(p1)); b = mk(hi(p1), lo(p2), hi(p2));
+}
 
 // The rare collider groups of one body, out of line (one copy, register-passed arguments) so the substep loop
 // stays small enough for the instruction cache:
@@ -307,10 +323,10 @@ __device__ __forceinline__ bool wall_single(const Body& b, V3 e, float rad, floa
   const V3 dvec = t0 ? da : db, bp = t0 ? ca : cb;
   const float d2 = dot(dvec, dvec), rs = rad + 1e-6f;
   if (d2 < rs * rs) {
-    const float dist = sqrtf(d2);
+    const float dist = sqrt_pos(d2);
     const float pen = rad - dist;
     if (pen > 0.0f) {
-      const V3 n = __fdividef(1.0f, 1e-6f + dist) * dvec;
+      const V3 n = rcp_ftz(1e-6f + dist) * dvec;
       const V3 rel = bp - b.p;
       c = impulse(rel, b.v + cross(b.w, rel), n, pen, inv_m, C.baumgarte, C.friction, C.elasticity);
     }
@@ -431,6 +447,233 @@ __device__ __forceinline__ void substep(Rig& r, const LegK& k, float act_h, floa
   r.B.w = fma3(C.ang_damp, r.B.w, dwB);
   // ---- colliders on the post-potential state + integrators.collision; impulses accumulate into Info.contact
   contacts<WALLS>(r, C, dA, dB, mT, mA, mB, leg, acc);
+}
+
+// =====================================================================================================
+// Packed substep: the lane's Aux (A) and lower leg (B) travel as the two halves of float32x2 registers, so every
+// operation the two bodies share -- kinetic update, rotation columns, lever arms, joint anchors, spring/damper
+// forces, torques, the atan2 polynomial, the impulse application -- issues once (FFMA2 / FADD2 / FMUL2) instead
+// of twice. The step kernels are issue-bound, so this is where their time goes. The torso stays scalar.
+// Same algorithm and the same per-operation rounding as the scalar path; only the association of a few sums
+// differs (parity bars in tests/_parity.py).
+struct Rig2 { Body T; Body2 L; };  // L: lo = Aux, hi = lower leg
+
+__device__ __forceinline__ Rig2 pack_rig(const Rig& r) {
+  Rig2 o;
+  o.T = r.T;
+  o.L.p = pk3(r.A.p, r.B.p); o.L.v = pk3(r.A.v, r.B.v); o.L.w = pk3(r.A.w, r.B.w);
+  o.L.qw = pk(r.A.qw, r.B.qw); o.L.qx = pk(r.A.qx, r.B.qx); o.L.qy = pk(r.A.qy, r.B.qy); o.L.qz = pk(r.A.qz, r.B.qz);
+  return o;
+}
+__device__ __forceinline__ Rig unpack_rig(const Rig2& r) {
+  Rig o;
+  o.T = r.T;
+  o.A.p = lo3(r.L.p); o.A.v = lo3(r.L.v); o.A.w = lo3(r.L.w);
+  o.A.qw = lo(r.L.qw); o.A.qx = lo(r.L.qx); o.A.qy = lo(r.L.qy); o.A.qz = lo(r.L.qz);
+  o.B.p = hi3(r.L.p); o.B.v = hi3(r.L.v); o.B.w = hi3(r.L.w);
+  o.B.qw = hi(r.L.qw); o.B.qx = hi(r.L.qx); o.B.qy = hi(r.L.qy); o.B.qz = hi(r.L.qz);
+  return o;
+}
+
+
+__device__ __forceinline__ void kinetic_t(Body& b, float h) {  // `kinetic` with the bare MUFU.RSQ
+  b.p.x = fmaf(b.v.x, h, b.p.x);
+  b.p.y = fmaf(b.v.y, h, b.p.y);
+  b.p.z = fmaf(b.v.z, h, b.p.z);
+  const float hh = 0.5f * h;
+  const float ax = b.w.x * hh, ay = b.w.y * hh, az = b.w.z * hh;
+  const float w = b.qw - ax * b.qx - ay * b.qy - az * b.qz;
+  const float x = b.qx + ax * b.qw + ay * b.qz - az * b.qy;
+  const float y = b.qy - ax * b.qz + ay * b.qw + az * b.qx;
+  const float z = b.qz + ax * b.qy - ay * b.qx + az * b.qw;
+  const float r = rsqrt_ftz(w * w + x * x + y * y + z * z);
+  b.qw = w * r; b.qx = x * r; b.qy = y * r; b.qz = z * r;
+}
+
+__device__ __forceinline__ void kinetic2(Body2& b, float h) {
+  b.p = fma3(h, b.v, b.p);
+  const float hh = 0.5f * h;
+  const F2 ax = hh * b.w.x, ay = hh * b.w.y, az = hh * b.w.z;
+  const F2 w = fnma2(az, b.qz, fnma2(ay, b.qy, fnma2(ax, b.qx, b.qw)));
+  const F2 x = fnma2(az, b.qy, fma2(ay, b.qz, fma2(ax, b.qw, b.qx)));
+  const F2 y = fma2(az, b.qx, fma2(ay, b.qw, fnma2(ax, b.qz, b.qy)));
+  const F2 z = fma2(az, b.qw, fnma2(ay, b.qx, fma2(ax, b.qy, b.qz)));
+  const F2 n2 = fma2(z, z, fma2(y, y, fma2(x, x, w * w)));
+  const F2 r = pk(rsqrt_ftz(lo(n2)), rsqrt_ftz(hi(n2)));
+  b.qw = w * r; b.qx = x * r; b.qy = y * r; b.qz = z * r;
+}
+
+__device__ __forceinline__ Cols2 rot_cols2(const Body2& b) {
+  const F2 s = b.qw, x = b.qx, y = b.qy, z = b.qz;
+  const F2 x2 = x + x, y2 = y + y, z2 = z + z, s2 = s + s;
+  const F2 d = fms2(s, s, fma2(z, z, fma2(y, y, x * x)));
+  const F2 sx = s2 * x, sy = s2 * y, sz = s2 * z;
+  Cols2 c;
+  c.c0 = mk2(fma2(x2, x, d), fma2(x2, y, sz), fms2(x2, z, sy));
+  c.c1 = mk2(fms2(y2, x, sz), fma2(y2, y, d), fma2(y2, z, sx));
+  c.c2 = mk2(fma2(z2, x, sy), fms2(z2, y, sx), fma2(z2, z, d));
+  return c;
+}
+
+// atan2_fast for two (y, x) pairs: the polynomial runs packed, the octant logic per half.
+__device__ __forceinline__ F2 atan2_fast2(F2 y, F2 x) {
+  const float xl = lo(x), xh = hi(x), yl = lo(y), yh = hi(y);
+  const float axl = fabsf(xl), ayl = fabsf(yl), axh = fabsf(xh), ayh = fabsf(yh);
+  const F2 mn = pk(fminf(axl, ayl), fminf(axh, ayh));
+  const F2 t = mn * pk(rcp_ftz(fmaxf(axl, ayl)), rcp_ftz(fmaxf(axh, ayh)));
+  const F2 s = t * t;
+  F2 p = bc(-0.004054381512105465f);
+  p = fma2(p, s, bc(0.021862255409359932f));
+  p = fma2(p, s, bc(-0.055911269038915634f));
+  p = fma2(p, s, bc(0.09642115980386734f));
+  p = fma2(p, s, bc(-0.13908596336841583f));
+  p = fma2(p, s, bc(0.1994655877351761f));
+  p = fma2(p, s, bc(-0.33329859375953674f));
+  p = fma2(p, s, bc(0.9999993443489075f));
+  const F2 r = p * t;
+  float rl = lo(r), rh = hi(r);
+  rl = ayl > axl ? 1.57079632679489662f - rl : rl;
+  rh = ayh > axh ? 1.57079632679489662f - rh : rh;
+  rl = xl < 0.0f ? 3.14159265358979324f - rl : rl;
+  rh = xh < 0.0f ? 3.14159265358979324f - rh : rh;
+  return pk(copysignf(rl, yl), copysignf(rh, yh));
+}
+
+// limit_and_actuator for (hip, ankle): lim_lo / lim_hi = the two joints' limits, act_h = h * strength * action.
+// dang = min(hi - psi, 0) + max(lo - psi, 0) is the limit violation (exactly 0 inside the limits), and the
+// actuator torque is cut off whenever it is non-zero.
+__device__ __forceinline__ F2 limit_and_actuator2(F2 sin_psi, F2 cos_psi, F2 lim_lo, F2 lim_hi, F2 act_h, float h_ls) {
+  const F2 psi = atan2_fast2(sin_psi, cos_psi);
+  const F2 a = lim_hi - psi, b = lim_lo - psi;
+  const F2 dang = pk(fminf(lo(a), 0.0f), fminf(hi(a), 0.0f)) + pk(fmaxf(lo(b), 0.0f), fmaxf(hi(b), 0.0f));
+  const F2 t = pk(lo(dang) == 0.0f ? lo(act_h) : 0.0f, hi(dang) == 0.0f ? hi(act_h) : 0.0f);
+  return fma2(h_ls, dang, t);
+}
+
+template <bool WALLS>
+__device__ __forceinline__ void contacts2(Rig2& r, const DevConst& C, V3 dA, V3 dB, unsigned mT, unsigned mA,
+                                          unsigned mB, int leg, ContactAcc& acc) {
+  Body A, B;  // scalar views of the two halves (only v / w are written back)
+  A.p = lo3(r.L.p); A.v = lo3(r.L.v); A.w = lo3(r.L.w);
+  B.p = hi3(r.L.p); B.v = hi3(r.L.v); B.w = hi3(r.L.w);
+  V3 gv, gw;
+  foot_ground(B, C.s_foot * dB, C.r_leg, C.inv_m_leg, C, gv, gw);
+  const bool hitT = C.r_torso - r.T.p.z > 0.0f;
+  if (__builtin_expect(hitT || (WALLS && (mT | mA | mB) != 0u), 0)) {  // the one divergent region of the substep (rare)
+    const V3 zero = mk(0.f, 0.f, 0.f);
+    if (hitT || mT != 0u) {
+      Imp t;
+      t.dv = t.dw = zero;
+      if (hitT)
+        t = rare_group(r.T.p, zero, r.T.v, r.T.w, C.r_torso, 0.0f, C.inv_m_torso, 0u, C.walls, C.baumgarte, C.friction,
+                       C.elasticity);
+      if (WALLS && mT != 0u) {
+        Imp c;
+        if (!wall_single(r.T, zero, C.r_torso, C.inv_m_torso, mT, C, c))
+          c = wall_group(r.T, zero, C.r_torso, C.r_torso + 1e-4f, C.inv_m_torso, mT, C);
+        t.dv += c.dv; t.dw += c.dw;
+      }
+      r.T.v += t.dv; r.T.w += t.dw;
+      if (leg == 0) { row_add(acc.cv, 0, t.dv); row_add(acc.ca, 0, t.dw); }
+    }
+    if (WALLS && mA != 0u) {
+      Imp c;
+      if (!wall_single(A, C.s_aux * dA, C.r_leg, C.inv_m_leg, mA, C, c))
+        c = wall_group(A, C.s_aux * dA, C.r_leg, C.seg_aux + C.r_leg + 1e-4f, C.inv_m_leg, mA, C);
+      A.v += c.dv; A.w += c.dw;
+      row_add(acc.cv, 1 + 2 * leg, c.dv); row_add(acc.ca, 1 + 2 * leg, c.dw);
+    }
+    if (WALLS && mB != 0u) {
+      Imp c;
+      if (!wall_single(B, C.s_foot * dB, C.r_leg, C.inv_m_leg, mB, C, c))
+        c = wall_group(B, C.s_foot * dB, C.r_leg, C.seg_foot + C.r_leg + 1e-4f, C.inv_m_leg, mB, C);
+      B.v += c.dv; B.w += c.dw;
+      acc.Bv += c.dv; acc.Bw += c.dw;
+    }
+  }
+  B.v += gv; B.w += gw;
+  acc.Bv += gv; acc.Bw += gw;
+  r.L.v = pk3(A.v, B.v); r.L.w = pk3(A.w, B.w);
+}
+
+template <bool WALLS>
+__device__ __forceinline__ void advance2(Rig2& r, const DevConst& C, unsigned& mT, unsigned& mA, unsigned& mB) {
+  kinetic_t(r.T, C.h);
+  kinetic2(r.L, C.h);
+  mT = mA = mB = 0u;
+  if (WALLS && C.n_walls > 0) {
+    mT = wall_mask_at(C, 0, r.T.p.x, r.T.p.y);
+    mA = wall_mask_at(C, 1, lo(r.L.p.x), lo(r.L.p.y));
+    mB = wall_mask_at(C, 2, hi(r.L.p.x), hi(r.L.p.y));
+  }
+}
+
+// Loop-invariant packed constants of the lane.
+struct LegK2 {
+  F2 sc;              // child-side joint offset scales (s_hip_c, s_ank_c)
+  F2 lim_lo, lim_hi;  // (hip, ankle) limits
+  F2 act_h;           // h * strength * (hip action, ankle action)
+};
+__device__ __forceinline__ LegK2 leg_consts2(const DevConst& C, const LegK& k, float act_hip, float act_ank) {
+  LegK2 q;
+  q.sc = pk(C.s_hip_c, C.s_ank_c);
+  q.lim_lo = pk(C.hip_lo, k.alo); q.lim_hi = pk(C.hip_hi, k.ahi);
+  q.act_h = pk(act_hip * C.h_act, act_ank * C.h_act);
+  return q;
+}
+
+// One physics substep for the lane's three bodies after `advance2` (integrators.kinetic) has run.
+// All impulses carry the factor h (C.h_k = h*stiffness, ...), so `potential` is a plain add.
+template <bool WALLS>
+__device__ __forceinline__ void substep2(Rig2& r, const LegK& k, const LegK2& k2, const DevConst& C, int leg,
+                                         unsigned mT, unsigned mA, unsigned mB, ContactAcc& acc) {
+  const Cols cT = rot_cols(r.T);
+  const Cols2 cL = rot_cols2(r.L);
+  // R u: every lever arm of the leg is a scalar times dT / dA / dB
+  const V3 dT = k.ux * cT.c0 + k.uy * cT.c1;
+  const V3x2 dL = fma3(k.uy, cL.c1, k.ux * cL.c0);
+  const V3 xT = cross(r.T.w, dT);
+  const V3x2 xL = cross(r.L.w, dL);
+  const V3 dA = lo3(dL), xA = lo3(xL);
+  // ---- joint anchors: child side packed (A at the hip, B at the ankle), parent side (T at the hip, A at the
+  // ankle) scalar into fresh pairs. G = h*F on the child, (hip, ankle).
+  const V3x2 cp = fma3(k2.sc, dL, r.L.p), cv = fma3(k2.sc, xL, r.L.v);
+  const V3 pph = fma3(C.s_hip_p, dT, r.T.p), ppa = fma3(C.s_ank_p, dA, lo3(r.L.p));
+  const V3 pvh = fma3(C.s_hip_p, xT, r.T.v), pva = fma3(C.s_ank_p, xA, lo3(r.L.v));
+  const V3x2 ep = pk3(pph, ppa) - cp, ev = pk3(pvh, pva) - cv;
+  const V3x2 G = fma3(C.h_sd, ev, C.h_k * ep);
+  // ---- joint angles. hip: axis e_z, ref -e_x: psi = atan2(c0_A.c1_T, c0_A.c0_T) (the triple product
+  // (c0_T x c0_A).c2_T equals c0_A.(c2_T x c0_T)). ankle: axis (cos phi, sin phi, 0), ref e_z:
+  // (c2_A x c2_B).axA = c2_B.nA with nA = axA x c2_A.
+  const V3 cA0 = lo3(cL.c0), cA1 = lo3(cL.c1), cA2 = lo3(cL.c2), cB2 = hi3(cL.c2);
+  const V3x2 ax = fma3(k.axs, cL.c1, k.axc * cL.c0);  // (axA, axB)
+  const V3 axA = lo3(ax), axB = hi3(ax);
+  const V3 nA = k.axs * cA0 - k.axc * cA1;
+  const F2 s = limit_and_actuator2(pk(dot(cA0, cT.c1), dot(cB2, nA)), pk(dot(cA0, cT.c0), dot(cA2, cB2)), k2.lim_lo,
+                                   k2.lim_hi, k2.act_h, C.h_ls);
+  // ---- h*torque on the parent, (hip, ankle): -ad*(w_p - w_c) - s*axis_p + k*(axis_p x axis_c)
+  const V3 wA = lo3(r.L.w);
+  const V3x2 t = fma3(-C.h_ad, pk3(r.T.w - wA, wA - hi3(r.L.w)),
+                      fma3(neg(s), pk3(cT.c2, axA), C.h_k * pk3(cross(cT.c2, cA2), cross(axA, axB))));
+  // ---- joint impulses (x h): parent (-F/m, rp x -F + tau), child (F/m, rc x F - tau); torso summed over legs
+  const V3 Gh = lo3(G), Ga = hi3(G), ta = hi3(t);
+  V3 sG = Gh, dwT = fma3(-C.s_hip_p, cross(dT, Gh), lo3(t));
+  quad_sum2(sG, dwT);
+  // ---- integrators.potential: vel = exp(vdamp h) vel + (dv + g) h ; ang = exp(adamp h) ang + dw h
+  if (C.vel_damp != 1.0f) { r.T.v = C.vel_damp * r.T.v; r.L.v = C.vel_damp * r.L.v; }
+  r.T.v = fma3(-C.inv_m_torso, sG, r.T.v); r.T.v.z += C.h_g;
+  r.T.w = fma3(C.ang_damp, r.T.w, dwT);
+  V3x2 v = fma3(C.inv_m_leg, G, r.L.v);                    // A: +Gh/m (then -Ga/m below), B: +Ga/m
+  v.z = v.z + bc(C.h_g);
+  V3x2 arm = k2.sc * G;                                    // A: s_hip_c*Gh (then -s_ank_p*Ga), B: s_ank_c*Ga
+  const V3 vA = fma3(-C.inv_m_leg, Ga, lo3(v)), armA = fma3(-C.s_ank_p, Ga, lo3(arm));
+  v = pk3(vA, hi3(v)); arm = pk3(armA, hi3(arm));
+  V3x2 dw = cross(dL, arm) - t;                            // A: ... - th (then + ta), B: ... - ta
+  dw = pk3(lo3(dw) + ta, hi3(dw));
+  r.L.v = v;
+  r.L.w = fma3(C.ang_damp, r.L.w, dw);
+  // ---- colliders on the post-potential state + integrators.collision; impulses accumulate into Info.contact
+  contacts2<WALLS>(r, C, dA, hi3(dL), mT, mA, mB, leg, acc);
 }
 
 // ---- packed state load / store (layout in dev_const.h) -------------------------------------------

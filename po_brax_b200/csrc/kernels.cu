@@ -18,6 +18,9 @@
 
 namespace pobrax {
 
+#ifndef POBRAX_WALL_WARPS_PER_SMSP
+#define POBRAX_WALL_WARPS_PER_SMSP 4      // resident warps per SM sub-partition the wall variants are compiled for
+#endif
 constexpr int kThreads = 128;             // reset kernels
 constexpr int kEnvsPerBlock = kThreads / 4;
 // Step kernels use small CTAs (1-2 warps): warps never wait for each other, so finer CTAs let the hardware
@@ -25,7 +28,7 @@ constexpr int kEnvsPerBlock = kThreads / 4;
 template <int KIND> struct StepCfg {
   static constexpr int threads = (KIND == POBRAX_ANT || KIND == POBRAX_ANT_TAG) ? 32 : 64;
   static constexpr int envs = threads / 4;
-  static constexpr int min_blocks = (KIND == POBRAX_ANT ? 5 : 4) * (128 / threads);   // 96 / 128 registers
+  static constexpr int min_blocks = (KIND == POBRAX_ANT ? 5 : POBRAX_WALL_WARPS_PER_SMSP) * (128 / threads);  // 96 / 128 registers
 };
 
 // ------------------------------------------------------------------------------------------- helpers
@@ -231,14 +234,18 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
     // Rotated substep loop, one code copy of each half (the kernel must fit the instruction cache):
     // iteration s runs the dynamics of substep s-1 and then the kinetic update + wall-mask loads of substep s,
     // so the three table loads are in flight during the next iteration's joint math.
+    // Inside the loop the Aux and the lower leg are the two halves of packed float32x2 registers (Rig2).
     constexpr bool W = KIND != POBRAX_ANT;
     unsigned mT = 0u, mA = 0u, mB = 0u;
     const int nsub = C.substeps;
+    const LegK2 k2 = leg_consts2(C, k, act.x, act.y);
+    Rig2 p = pack_rig(r);
 #pragma unroll 1
     for (int s = 0; s <= nsub; ++s) {
-      if (s > 0) substep<W>(r, k, act.x, act.y, C, leg, mT, mA, mB, acc);
-      if (s < nsub) advance<W>(r, C, mT, mA, mB);
+      if (s > 0) substep2<W>(p, k, k2, C, leg, mT, mA, mB, acc);
+      if (s < nsub) advance2<W>(p, C, mT, mA, mB);
     }
+    r = unpack_rig(p);
   }
 
   __syncwarp();

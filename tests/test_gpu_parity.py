@@ -345,14 +345,20 @@ def test_randomized_autoreset_naive(kind):
     w = RandomizedAutoResetWrapperNaive(envs.create(kind, batch_size=n, episode_length=L, auto_reset=False))
     cs = w.reset(keys)
     rng = tf.prng_key(4)
+    o.env.sys.track_margin = True
+    dirty = np.zeros(n, bool)   # free-running: an env that passed a rounding-ambiguous branch stays out until it resets
     for t in range(T):
         rng, a = P.actions_for(rng, n)
+        o.env.sys.margin = None
         s = o.step(s, a)
         cs = w.step(cs, torch.as_tensor(a, device='cuda'))
+        dirty |= o.step_margin <= P.BRANCH_MARGIN
+        dirty &= ~np.asarray(s.done, bool)   # done: qp is a fresh reset again
         assert np.array_equal(P.t2n(cs.info['steps']), s.info['steps']), t
-        assert np.array_equal(P.t2n(cs.done), np.asarray(s.done, np.float32)), t
+        assert np.array_equal(P.t2n(cs.done)[~dirty], np.asarray(s.done, np.float32)[~dirty]), t
         assert (P.rng_bits(cs.info['rng']) == s.info['rng']).all()
-        P.assert_qp_close(cs.qp, s.qp, f'{kind} randomized autoreset t={t}', vel_atol=5e-3, pos_scale=10.0)
+        P.assert_qp_close(cs.qp, s.qp, f'{kind} randomized autoreset t={t}', vel_atol=5e-3, pos_scale=10.0, rows=~dirty)
+        assert (~dirty).mean() >= 0.6   # up to L = 3 free-running steps of accumulated ambiguity
         if (t + 1) % L == 0:  # every env just hit the episode limit: qp is a fresh reset, bit-exact frozen bodies
             assert np.array_equal(P.t2n(cs.qp.pos)[:, 10:], s.qp.pos[:, 10:])
 

@@ -1,12 +1,14 @@
 """Per-env step time (1 Mi envs, 40 timed steps after 10 warm-up steps), walls on / off (test hook):
-    python tools/bench_envs.py
+    python tools/bench_envs.py [env ...]          (POBRAX_LIB=<tuning build> to time another build)
 """
 import sys, time, torch
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from po_brax_b200 import envs
 from po_brax_b200.parallel import shard_keys
 n=1<<20
-for name,kw in (('ant_tag',{}),('ant_tag',{'walls':False}),('ant_heavenhell',{}),('ant_heavenhell',{'walls':False}),('ant_gather',{}),('ant_gather',{'walls':False}),('ant',{})):
+cases=(('ant_tag',{}),('ant_tag',{'walls':False}),('ant_heavenhell',{}),('ant_heavenhell',{'walls':False}),('ant_gather',{}),('ant_gather',{'walls':False}),('ant',{}))
+if len(sys.argv)>1: cases=[(a,{}) for a in sys.argv[1:]]
+for name,kw in cases:
     env=envs.create(name,batch_size=n,**kw)
     s=env.reset(shard_keys(env,0,n,0,1))
     g=torch.Generator(device='cuda').manual_seed(1)

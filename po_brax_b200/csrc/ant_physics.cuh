@@ -186,7 +186,7 @@ __device__ __forceinline__ Imp contact_general(V3 p, V3 e, V3 v, V3 w, float rad
   const V3 sp = a + t * d;
   const V3 bp = clamp3(sp, lo, hi);
   const V3 dvec = sp - bp;
-  const float dist = sqrtf(dot(dvec, dvec));
+  const float dist = sqrt_pos(dot(dvec, dvec));
   const float pen = rad - dist;
   if (!(pen > 0.0f)) {
     Imp o;
@@ -194,7 +194,7 @@ __device__ __forceinline__ Imp contact_general(V3 p, V3 e, V3 v, V3 w, float rad
     o.hit = 0.0f;
     return o;
   }
-  const V3 n = (1.0f / (1e-6f + dist)) * dvec;
+  const V3 n = rcp_ftz(1e-6f + dist) * dvec;
   const V3 rel = bp - p;
   return impulse(rel, v + cross(w, rel), n, pen, inv_m, baumgarte, friction, elasticity);
 }
@@ -568,18 +568,15 @@ __device__ __forceinline__ void contacts2(Rig2& r, const DevConst& C, V3 dA, V3 
         t = rare_group(r.T.p, zero, r.T.v, r.T.w, C.r_torso, 0.0f, C.inv_m_torso, 0u, C.walls, C.baumgarte, C.friction,
                        C.elasticity);
       if (WALLS && mT != 0u) {
-        Imp c;
-        if (!wall_single(r.T, zero, C.r_torso, C.inv_m_torso, mT, C, c))
-          c = wall_group(r.T, zero, C.r_torso, C.r_torso + 1e-4f, C.inv_m_torso, mT, C);
+        // torso and Aux near a wall are rare (the lower legs reach furthest): no inline fast path, one code copy
+        const Imp c = wall_group(r.T, zero, C.r_torso, C.r_torso + 1e-4f, C.inv_m_torso, mT, C);
         t.dv += c.dv; t.dw += c.dw;
       }
       r.T.v += t.dv; r.T.w += t.dw;
       if (leg == 0) { row_add(acc.cv, 0, t.dv); row_add(acc.ca, 0, t.dw); }
     }
     if (WALLS && mA != 0u) {
-      Imp c;
-      if (!wall_single(A, C.s_aux * dA, C.r_leg, C.inv_m_leg, mA, C, c))
-        c = wall_group(A, C.s_aux * dA, C.r_leg, C.seg_aux + C.r_leg + 1e-4f, C.inv_m_leg, mA, C);
+      const Imp c = wall_group(A, C.s_aux * dA, C.r_leg, C.seg_aux + C.r_leg + 1e-4f, C.inv_m_leg, mA, C);
       A.v += c.dv; A.w += c.dw;
       row_add(acc.cv, 1 + 2 * leg, c.dv); row_add(acc.ca, 1 + 2 * leg, c.dw);
     }

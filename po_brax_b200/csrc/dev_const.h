@@ -35,6 +35,7 @@ struct DevConst {
   int32_t n_envs, env_kind, nb, obs_dim, aux_dim, metrics_dim;   // obs_dim: full row (staging stride)
   int32_t obs_lo, obs_out;                   // emitted columns [obs_lo, obs_lo + obs_out); obs_out == obs_dim: all
   int32_t episode_length, auto_reset, substeps, track_metrics, n_walls, has_rng;
+  int32_t prefetch_ctas;                     // step kernel: L2 prefetch distance in CTAs (0: this CTA's own, harmless)
   float h, dt, gravity_z, vel_damp, ang_damp, baumgarte, friction, elasticity;
   float m_torso, m_leg, inv_m_torso, inv_m_leg, r_torso, r_leg;
   float k_joint, sd_joint, ad_joint, ls_joint, act_strength;

@@ -10,6 +10,7 @@
 //
 // Thread mapping: 4 lanes = 1 env (lane l owns leg l and a replica of the torso); a warp = 8 envs.
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <math_constants.h>
 
 #include "../../include/pobrax.h"
@@ -40,6 +41,7 @@ __device__ __forceinline__ float ld_now(const float* p) {
   asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // jp.norm of a 2-vector without FMA contraction (keeps <= radius tests identical to the CPU oracle's)
 __device__ __forceinline__ float norm2_rn(float dx, float dy) {
   return sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
@@ -201,10 +203,26 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
   Rig r;
   load_rig(reinterpret_cast<const float4*>(S.qp), n, e, leg, r);
   const float2 act = reinterpret_cast<const float2*>(action)[e * 4 + leg];
-  float steps = ld_now(S.steps + e);
-  float done_prev = ld_now(S.done + e);
-  float ep_ret = C.track_metrics ? ld_now(S.ep_return + e) : 0.0f;
-  float aux_side = (KIND == POBRAX_ANT_HEAVENHELL) ? ld_now(S.aux + 2 * n + e) : 0.0f;
+  // The episode scalars are only needed behind the substep loop: pull them into L2 now, load them there (their
+  // L2 latency hides behind the observation math) instead of holding registers across the loop.
+  if (leg == 0) {
+    prefetch_l2(S.steps + e); prefetch_l2(S.done + e);
+    if (C.track_metrics) prefetch_l2(S.ep_return + e);
+    if (KIND == POBRAX_ANT_HEAVENHELL) prefetch_l2(S.aux + 2 * n + e);
+  }
+  // DRAM -> L2 prefetch of the state a CTA `prefetch_ctas` further on will load (CTAs start roughly in index
+  // order): its prologue then waits for an L2 hit instead of a DRAM access.
+  {
+    const size_t ep = e + (size_t)C.prefetch_ctas * StepCfg<KIND>::envs;
+    if (ep < n) {
+      const float4* q = reinterpret_cast<const float4*>(S.qp);
+      prefetch_l2(q + (size_t)leg * n + ep);                           // 4 torso planes, one per lane of the quad
+      const float4* ql = q + (size_t)(4 + 7 * leg) * n + ep;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) prefetch_l2(ql + (size_t)i * n);
+      prefetch_l2(action + ep * 8 + 2 * leg);
+    }
+  }
   asm volatile("" ::: "memory");
   {
     float4* s4 = reinterpret_cast<float4*>(stage);  // 8 rows = 32*D bytes: a whole number of float4
@@ -213,7 +231,6 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
     for (int i = lane; i < 2 * D; i += 32) s4[i] = z;
   }
   __syncwarp();
-  if (C.auto_reset == POBRAX_AUTORESET_CACHED && done_prev != 0.0f) steps = 0.0f;  // AutoResetWrapper.step head
   const float x_before = r.T.p.x;
 
   // Tag: the opponent's move choice depends only on info['rng'] (ant_tag.py:131-132), not on the physics:
@@ -248,8 +265,13 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
     r = unpack_rig(p);
   }
 
+  float steps = ld_now(S.steps + e);
+  const float done_prev = ld_now(S.done + e);
+  const float ep_ret = C.track_metrics ? ld_now(S.ep_return + e) : 0.0f;
+  const float aux_side = (KIND == POBRAX_ANT_HEAVENHELL) ? ld_now(S.aux + 2 * n + e) : 0.0f;
   __syncwarp();
   stage_common_obs<KIND>(row, r, k, acc, leg, C);
+  if (C.auto_reset == POBRAX_AUTORESET_CACHED && done_prev != 0.0f) steps = 0.0f;  // AutoResetWrapper.step head
   const int extra = ObsCols<KIND>::cv + 6 * C.nb;
 
   // ---- task logic (computed redundantly by the 4 lanes from the replicated torso; lane 0 stores)
@@ -764,8 +786,20 @@ static cudaError_t launch_step_t(const DevConst& C, const PobraxState& S, const 
     cudaFuncSetAttribute(step_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr_set = true;
   }
+  // L2 prefetch distance: one full wave of resident CTAs ahead (POBRAX_PREFETCH_CTAS overrides, for tuning)
+  static int prefetch_ctas = -1;
+  if (prefetch_ctas < 0) {
+    int dev = 0, sms = 148, per_sm = StepCfg<KIND>::min_blocks;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<KIND>, StepCfg<KIND>::threads, smem);
+    const char* ov = getenv("POBRAX_PREFETCH_CTAS");
+    prefetch_ctas = ov ? atoi(ov) : sms * per_sm;
+  }
+  DevConst Cl = C;
+  Cl.prefetch_ctas = prefetch_ctas;
   const int blocks = (C.n_envs + StepCfg<KIND>::envs - 1) / StepCfg<KIND>::envs;
-  step_kernel<KIND><<<blocks, StepCfg<KIND>::threads, smem, st>>>(C, S, action);
+  step_kernel<KIND><<<blocks, StepCfg<KIND>::threads, smem, st>>>(Cl, S, action);
   return cudaGetLastError();
 }
 

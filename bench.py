@@ -25,7 +25,7 @@ FLOPS_PER_ENV_STEP = {'ant': 4.30e4, 'ant_heavenhell': 4.30e4, 'ant_tag': 4.30e4
 BYTES_PER_ENV_STEP = {'ant': 1332, 'ant_heavenhell': 1444, 'ant_tag': 1428, 'ant_gather': 2212}
 METRIC = 'env-steps/sec'
 # dram__bytes_read.sum + dram__bytes_write.sum of one step_kernel launch, from the committed ncu --set full capture
-# (profiles/ncu_step_hh_r1.txt: 587.8 MB read + 990.5 MB write at 1 Mi HeavenHell envs = 1505 B per env-step)
+# (profiles/ncu_step_hh_r1.txt: 593.4 MB read + 984.2 MB write at 1 Mi HeavenHell envs = 1505 B per env-step)
 NCU_TRAFFIC_BYTES_PER_LAUNCH = {('ant_heavenhell', 1 << 20): 1.578e9}
 
 

@@ -31,22 +31,6 @@ __device__ __forceinline__ Cols rot_cols(const Body& b) {
   return c;
 }
 
-// integrators.kinetic: pos += vel*h; rot += quat_mul((0, ang*0.5*h), rot); rot /= |rot|
-__device__ __forceinline__ void kinetic(Body& b, float h) {
-  b.p.x = fmaf(b.v.x, h, b.p.x);
-  b.p.y = fmaf(b.v.y, h, b.p.y);
-  b.p.z = fmaf(b.v.z, h, b.p.z);
-  const float hh = 0.5f * h;
-  const float ax = b.w.x * hh, ay = b.w.y * hh, az = b.w.z * hh;
-  const float w = b.qw - ax * b.qx - ay * b.qy - az * b.qz;
-  const float x = b.qx + ax * b.qw + ay * b.qz - az * b.qy;
-  const float y = b.qy - ax * b.qz + ay * b.qw + az * b.qx;
-  const float z = b.qz + ax * b.qy - ay * b.qx + az * b.qw;
-  const float n2 = w * w + x * x + y * y + z * z;
-  const float r = rsqrtf(n2);  // <= 2 ulp; the norm error does not accumulate (renormalised every substep)
-  b.qw = w * r; b.qx = x * r; b.qy = y * r; b.qz = z * r;
-}
-
 // atan2 for the joint-limit logic of the substep loop: octant reduction + degree-7 minimax polynomial in t^2
 // (max abs error 1.3e-7 rad incl. float32 rounding, i.e. the same 1-2 ulp class as atan2f, at ~40% of its
 // instruction count; no special-case handling: the arguments are products of unit vectors, never both zero).
@@ -67,17 +51,6 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
   r = ay > ax ? 1.57079632679489662f - r : r;
   r = x < 0.0f ? 3.14159265358979324f - r : r;
   return copysignf(r, y);
-}
-
-// Joint limit + actuator scalar of one joint: returns h*(limitStrength*dang + t) where dang is the limit
-// violation and t the actuator torque (zeroed outside the limits). SURVEY App. A.3 "joints"/"actuators".
-__device__ __forceinline__ float limit_and_actuator(float sin_psi, float cos_psi, float lo, float hi, float act,
-                                                    const DevConst& C) {
-  const float psi = atan2_fast(sin_psi, cos_psi);
-  const bool below = psi < lo, above = psi > hi;
-  const float dang = above ? hi - psi : (below ? lo - psi : 0.0f);
-  const float t = (below || above) ? 0.0f : act * C.h_act;
-  return fmaf(C.h_ls, dang, t);
 }
 
 // Joint angle and velocity for the observation (Revolute.angle_vel): psi as above, vel = (w_p - w_c).axis_p
@@ -334,128 +307,13 @@ __device__ __forceinline__ bool wall_single(const Body& b, V3 e, float rad, floa
   return true;
 }
 
-// Σ colliders.apply(qp) for the lane's bodies -- ground (torso sphere, foot end) + Arena walls (all three) --
-// evaluated on the state in `r`; then integrators.collision (vel += dv, ang += dw) and the Info.contact sums.
-// Every contact is evaluated on the same (pre-collision) state: a body's impulses are applied only after all
-// of that body's contacts have been evaluated. A body has at most one ground candidate, so the ground
-// group's "divide by the active count" is a no-op; the wall group divides per body.
-template <bool WALLS>
-__device__ __forceinline__ void contacts(Rig& r, const DevConst& C, V3 dA, V3 dB, unsigned mT, unsigned mA,
-                                         unsigned mB, int leg, ContactAcc& acc) {
-  V3 gv, gw;
-  foot_ground(r.B, C.s_foot * dB, C.r_leg, C.inv_m_leg, C, gv, gw);
-  const bool hitT = C.r_torso - r.T.p.z > 0.0f;
-  if (__builtin_expect(hitT || (WALLS && (mT | mA | mB) != 0u), 0)) {  // the one divergent region of the substep (rare)
-    const V3 zero = mk(0.f, 0.f, 0.f);
-    if (hitT || mT != 0u) {
-      Imp t;
-      t.dv = t.dw = zero;
-      if (hitT)
-        t = rare_group(r.T.p, zero, r.T.v, r.T.w, C.r_torso, 0.0f, C.inv_m_torso, 0u, C.walls, C.baumgarte, C.friction,
-                       C.elasticity);
-      if (WALLS && mT != 0u) {
-        Imp c;
-        if (!wall_single(r.T, zero, C.r_torso, C.inv_m_torso, mT, C, c))
-          c = wall_group(r.T, zero, C.r_torso, C.r_torso + 1e-4f, C.inv_m_torso, mT, C);
-        t.dv += c.dv; t.dw += c.dw;
-      }
-      r.T.v += t.dv; r.T.w += t.dw;
-      if (leg == 0) { row_add(acc.cv, 0, t.dv); row_add(acc.ca, 0, t.dw); }
-    }
-    if (WALLS && mA != 0u) {
-      Imp c;
-      if (!wall_single(r.A, C.s_aux * dA, C.r_leg, C.inv_m_leg, mA, C, c))
-        c = wall_group(r.A, C.s_aux * dA, C.r_leg, C.seg_aux + C.r_leg + 1e-4f, C.inv_m_leg, mA, C);
-      r.A.v += c.dv; r.A.w += c.dw;
-      row_add(acc.cv, 1 + 2 * leg, c.dv); row_add(acc.ca, 1 + 2 * leg, c.dw);
-    }
-    if (WALLS && mB != 0u) {
-      Imp c;
-      if (!wall_single(r.B, C.s_foot * dB, C.r_leg, C.inv_m_leg, mB, C, c))
-        c = wall_group(r.B, C.s_foot * dB, C.r_leg, C.seg_foot + C.r_leg + 1e-4f, C.inv_m_leg, mB, C);
-      r.B.v += c.dv; r.B.w += c.dw;
-      acc.Bv += c.dv; acc.Bw += c.dw;
-    }
-  }
-  r.B.v += gv; r.B.w += gw;
-  acc.Bv += gv; acc.Bw += gw;
-}
-
-// integrators.kinetic for the lane's bodies + (walls) the candidate-wall masks of the new positions. Run ahead
-// of the substep that consumes them, so the three table loads are in flight during the joint math.
-template <bool WALLS>
-__device__ __forceinline__ void advance(Rig& r, const DevConst& C, unsigned& mT, unsigned& mA, unsigned& mB) {
-  kinetic(r.T, C.h);
-  kinetic(r.A, C.h);
-  kinetic(r.B, C.h);
-  mT = mA = mB = 0u;
-  if (WALLS && C.n_walls > 0) {
-    mT = wall_mask_at(C, 0, r.T.p.x, r.T.p.y);
-    mA = wall_mask_at(C, 1, r.A.p.x, r.A.p.y);
-    mB = wall_mask_at(C, 2, r.B.p.x, r.B.p.y);
-  }
-}
-
-// One physics substep for the lane's three bodies after `advance` (integrators.kinetic) has run.
-// act_h / act_a: hip / ankle actions.
-// All impulses carry the factor h (C.h_k = h*stiffness, ...), so `potential` is a plain add.
-template <bool WALLS>
-__device__ __forceinline__ void substep(Rig& r, const LegK& k, float act_h, float act_a, const DevConst& C, int leg,
-                                        unsigned mT, unsigned mA, unsigned mB, ContactAcc& acc) {
-  const Cols cT = rot_cols(r.T), cA = rot_cols(r.A), cB = rot_cols(r.B);
-  const V3 dT = k.ux * cT.c0 + k.uy * cT.c1;  // R_T u: every lever arm of the leg is a scalar times dT / dA / dB
-  const V3 dA = k.ux * cA.c0 + k.uy * cA.c1;
-  const V3 dB = k.ux * cB.c0 + k.uy * cB.c1;
-  const V3 xT = cross(r.T.w, dT), xA = cross(r.A.w, dA), xB = cross(r.B.w, dB);
-  // ---- hip: Torso -> Aux, offsets s_hip_p*u / s_hip_c*u, axis e_z, ref -e_x
-  V3 Gh, th;  // Gh = h*F (on the child), th = h*torque (on the parent)
-  {
-    const V3 ep = fma3(-C.s_hip_c, dA, fma3(C.s_hip_p, dT, r.T.p - r.A.p));
-    const V3 ev = fma3(-C.s_hip_c, xA, fma3(C.s_hip_p, xT, r.T.v - r.A.v));
-    Gh = fma3(C.h_sd, ev, C.h_k * ep);
-    // psi = atan2((ref_p x ref_c).axis_p, ref_p.ref_c) with ref = -c0, axis_p = c2_T: the triple product
-    // (c0_T x c0_A).c2_T equals c0_A.(c2_T x c0_T) = c0_A.c1_T
-    const float s = limit_and_actuator(dot(cA.c0, cT.c1), dot(cA.c0, cT.c0), C.hip_lo, C.hip_hi, act_h, C);
-    th = fma3(-C.h_ad, r.T.w - r.A.w, fma3(-s, cT.c2, C.h_k * cross(cT.c2, cA.c2)));
-  }
-  // ---- ankle: Aux -> lower leg, axis (cos phi, sin phi, 0), ref e_z
-  V3 Ga, ta;
-  {
-    const V3 ep = fma3(-C.s_ank_c, dB, fma3(C.s_ank_p, dA, r.A.p - r.B.p));
-    const V3 ev = fma3(-C.s_ank_c, xB, fma3(C.s_ank_p, xA, r.A.v - r.B.v));
-    Ga = fma3(C.h_sd, ev, C.h_k * ep);
-    const V3 axA = k.axc * cA.c0 + k.axs * cA.c1;
-    const V3 axB = k.axc * cB.c0 + k.axs * cB.c1;
-    const V3 nA = k.axs * cA.c0 - k.axc * cA.c1;  // axA x c2_A, so (c2_A x c2_B).axA = c2_B.nA
-    const float s = limit_and_actuator(dot(cB.c2, nA), dot(cA.c2, cB.c2), k.alo, k.ahi, act_a, C);
-    ta = fma3(-C.h_ad, r.A.w - r.B.w, fma3(-s, axA, C.h_k * cross(axA, axB)));
-  }
-  // ---- joint impulses (x h): parent (-F/m, rp x -F + tau), child (F/m, rc x F - tau); torso summed over legs
-  const V3 dvT = quad_sum(-C.inv_m_torso * Gh);
-  const V3 dwT = quad_sum(fma3(-C.s_hip_p, cross(dT, Gh), th));
-  const V3 dvA = C.inv_m_leg * (Gh - Ga);
-  const V3 dwA = cross(dA, fma3(-C.s_ank_p, Ga, C.s_hip_c * Gh)) + (ta - th);
-  const V3 dvB = C.inv_m_leg * Ga;
-  const V3 dwB = fma3(C.s_ank_c, cross(dB, Ga), -ta);
-  // ---- integrators.potential: vel = exp(vdamp h) vel + (dv + g) h ; ang = exp(adamp h) ang + dw h
-  if (C.vel_damp != 1.0f) { r.T.v = C.vel_damp * r.T.v; r.A.v = C.vel_damp * r.A.v; r.B.v = C.vel_damp * r.B.v; }
-  r.T.v = r.T.v + dvT; r.T.v.z += C.h_g;
-  r.A.v = r.A.v + dvA; r.A.v.z += C.h_g;
-  r.B.v = r.B.v + dvB; r.B.v.z += C.h_g;
-  r.T.w = fma3(C.ang_damp, r.T.w, dwT);
-  r.A.w = fma3(C.ang_damp, r.A.w, dwA);
-  r.B.w = fma3(C.ang_damp, r.B.w, dwB);
-  // ---- colliders on the post-potential state + integrators.collision; impulses accumulate into Info.contact
-  contacts<WALLS>(r, C, dA, dB, mT, mA, mB, leg, acc);
-}
-
 // =====================================================================================================
 // Packed substep: the lane's Aux (A) and lower leg (B) travel as the two halves of float32x2 registers, so every
 // operation the two bodies share -- kinetic update, rotation columns, lever arms, joint anchors, spring/damper
 // forces, torques, the atan2 polynomial, the impulse application -- issues once (FFMA2 / FADD2 / FMUL2) instead
 // of twice. The step kernels are issue-bound, so this is where their time goes. The torso stays scalar.
-// Same algorithm and the same per-operation rounding as the scalar path; only the association of a few sums
-// differs (parity bars in tests/_parity.py).
+// Every packed operation rounds like its scalar counterpart (fma.rn / add.rn / mul.rn per half); parity bars in
+// tests/_parity.py.
 struct Rig2 { Body T; Body2 L; };  // L: lo = Aux, hi = lower leg
 
 __device__ __forceinline__ Rig2 pack_rig(const Rig& r) {
@@ -476,7 +334,9 @@ __device__ __forceinline__ Rig unpack_rig(const Rig2& r) {
 }
 
 
-__device__ __forceinline__ void kinetic_t(Body& b, float h) {  // `kinetic` with the bare MUFU.RSQ
+// integrators.kinetic: pos += vel*h; rot += quat_mul((0, ang*0.5*h), rot); rot /= |rot| (norm error <= 2 ulp, not
+// accumulating: renormalised every substep)
+__device__ __forceinline__ void kinetic_t(Body& b, float h) {
   b.p.x = fmaf(b.v.x, h, b.p.x);
   b.p.y = fmaf(b.v.y, h, b.p.y);
   b.p.z = fmaf(b.v.z, h, b.p.z);
@@ -550,6 +410,11 @@ __device__ __forceinline__ F2 limit_and_actuator2(F2 sin_psi, F2 cos_psi, F2 lim
   return fma2(h_ls, dang, t);
 }
 
+// Σ colliders.apply(qp) for the lane's bodies -- ground (torso sphere, foot end) + Arena walls (all three) --
+// evaluated on the state in `r`; then integrators.collision (vel += dv, ang += dw) and the Info.contact sums.
+// Every contact is evaluated on the same (pre-collision) state: a body's impulses are applied only after all
+// of that body's contacts have been evaluated. A body has at most one ground candidate, so the ground
+// group's "divide by the active count" is a no-op; the wall group divides per body.
 template <bool WALLS>
 __device__ __forceinline__ void contacts2(Rig2& r, const DevConst& C, V3 dA, V3 dB, unsigned mT, unsigned mA,
                                           unsigned mB, int leg, ContactAcc& acc) {

@@ -27,7 +27,11 @@ constexpr int kEnvsPerBlock = kThreads / 4;
 // Step kernels use small CTAs (1-2 warps): warps never wait for each other, so finer CTAs let the hardware
 // scheduler balance warps of different cost (wall contacts) and shorten the tail. Measured per env family.
 template <int KIND> struct StepCfg {
+#ifdef POBRAX_TUNE_THREADS   // tuning builds: one CTA size for every family
+  static constexpr int threads = POBRAX_TUNE_THREADS;
+#else
   static constexpr int threads = (KIND == POBRAX_ANT || KIND == POBRAX_ANT_TAG) ? 32 : 64;
+#endif
   static constexpr int envs = threads / 4;
   static constexpr int min_blocks = (KIND == POBRAX_ANT ? 5 : POBRAX_WALL_WARPS_PER_SMSP) * (128 / threads);  // 96 / 128 registers
 };
@@ -604,14 +608,14 @@ reset_kernel(const __grid_constant__ DevConst C, const PobraxState S, const uint
   {
     const Cols cA = rot_cols(r.A), cB = rot_cols(r.B);
     const V3 dA = k.ux * cA.c0 + k.uy * cA.c1, dB = k.ux * cB.c0 + k.uy * cB.c1;
-    Rig tmp = r;
+    Rig2 tmp = pack_rig(r);
     unsigned mT = 0u, mA = 0u, mB = 0u;
     if (KIND != POBRAX_ANT && C.n_walls > 0) {
       mT = wall_mask_at(C, 0, r.T.p.x, r.T.p.y);
       mA = wall_mask_at(C, 1, r.A.p.x, r.A.p.y);
       mB = wall_mask_at(C, 2, r.B.p.x, r.B.p.y);
     }
-    contacts<KIND != POBRAX_ANT>(tmp, C, dA, dB, mT, mA, mB, leg, ct);
+    contacts2<KIND != POBRAX_ANT>(tmp, C, dA, dB, mT, mA, mB, leg, ct);
   }
   __syncwarp();
   stage_common_obs<KIND>(row, r, k, ct, leg, C);

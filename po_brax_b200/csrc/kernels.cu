@@ -186,7 +186,11 @@ __device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, const fl
 
 // --------------------------------------------------------------------------------------------- step
 template <int KIND>
+#ifdef POBRAX_TUNE_MAXNREG   // tuning builds: cap the wall variants' registers directly
+__global__ void __launch_bounds__(StepCfg<KIND>::threads) __maxnreg__(KIND == POBRAX_ANT ? 96 : POBRAX_TUNE_MAXNREG)
+#else
 __global__ void __launch_bounds__(StepCfg<KIND>::threads, StepCfg<KIND>::min_blocks)
+#endif
 step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float* __restrict__ action) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

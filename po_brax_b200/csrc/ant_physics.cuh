@@ -53,13 +53,6 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
   return copysignf(r, y);
 }
 
-// Joint angle and velocity for the observation (Revolute.angle_vel): psi as above, vel = (w_p - w_c).axis_p
-__device__ __forceinline__ void joint_angle_vel(const Body& P, const Body& Cb, V3 axis_p, V3 ref_p, V3 ref_c,
-                                                float& psi, float& vel) {
-  psi = atan2_fast(dot(cross(ref_p, ref_c), axis_p), dot(ref_p, ref_c));
-  vel = dot(P.w - Cb.w, axis_p);
-}
-
 // Bare MUFU.RSQ / MUFU.RCP (no denormal-range fix-up code): the arguments here are never denormal -- quaternion
 // norms, 1/m + lever^2, 1e-6 + |v|, max(|sin|, |cos|). sqrt_pos: sqrt to ~2 ulp for lengths (0 below 1e-15).
 __device__ __forceinline__ float rsqrt_ftz(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }

@@ -84,11 +84,18 @@ template <int KIND>
 __device__ __forceinline__ void stage_common_obs(float* row, const Rig& r, const LegK& k, const ContactAcc& acc, int leg,
                                                  const DevConst& C) {
   using O = ObsCols<KIND>;
-  const Cols cT = rot_cols(r.T), cA = rot_cols(r.A), cB = rot_cols(r.B);
-  float jah, jvh, jaa, jva;
-  joint_angle_vel(r.T, r.A, cT.c2, cT.c0, cA.c0, jah, jvh);
-  const V3 axA = k.axc * cA.c0 + k.axs * cA.c1;
-  joint_angle_vel(r.A, r.B, axA, cA.c2, cB.c2, jaa, jva);
+  // Revolute.angle_vel of the hip and the ankle, the two joints packed like in the substep:
+  // hip psi = atan2(c0_A.c1_T, c0_A.c0_T), ankle psi = atan2(c2_B.(axA x c2_A), c2_A.c2_B); vel = (w_p - w_c).axis_p
+  const Cols cT = rot_cols(r.T);
+  Body2 L;
+  L.qw = pk(r.A.qw, r.B.qw); L.qx = pk(r.A.qx, r.B.qx); L.qy = pk(r.A.qy, r.B.qy); L.qz = pk(r.A.qz, r.B.qz);
+  const Cols2 cL = rot_cols2(L);
+  const V3 cA0 = lo3(cL.c0), cA1 = lo3(cL.c1), cA2 = lo3(cL.c2), cB2 = hi3(cL.c2);
+  const V3 axA = k.axc * cA0 + k.axs * cA1;
+  const V3 nA = k.axs * cA0 - k.axc * cA1;
+  const F2 psi = atan2_fast2(pk(dot(cA0, cT.c1), dot(cB2, nA)), pk(dot(cA0, cT.c0), dot(cA2, cB2)));
+  const float jah = lo(psi), jaa = hi(psi);
+  const float jvh = dot(r.T.w - r.A.w, cT.c2), jva = dot(r.A.w - r.B.w, axA);
   row[O::ja + 2 * leg] = jah; row[O::ja + 2 * leg + 1] = jaa;
   row[O::jv + 2 * leg] = jvh; row[O::jv + 2 * leg + 1] = jva;
   float* cv = acc.cv;
@@ -165,8 +172,8 @@ __device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, const fl
     const int n4 = (rows * D) >> 2;
     const float4* s4 = reinterpret_cast<const float4*>(stage);
     float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll 1
-    for (int i = lane; i < n4; i += 32) d4[i] = s4[i];
+#pragma unroll 4
+    for (int i = lane; i < n4; i += 32) d4[i] = s4[i];   // unrolled: 4 LDS.128 in flight before the first STG.128
 #pragma unroll 1
     for (int i = 4 * n4 + lane; i < rows * D; i += 32) dst[i] = stage[i];
   } else {

@@ -224,6 +224,12 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
     prefetch_l2(S.steps + e); prefetch_l2(S.done + e);
     if (C.track_metrics) prefetch_l2(S.ep_return + e);
     if (KIND == POBRAX_ANT_HEAVENHELL) prefetch_l2(S.aux + 2 * n + e);
+    if (KIND == POBRAX_ANT_TAG) { prefetch_l2(S.aux + 2 * n + e); prefetch_l2(S.aux + 3 * n + e); }
+  }
+  if (KIND == POBRAX_ANT_GATHER) {  // the lane's 4 objects (read behind the loop)
+#pragma unroll
+    for (int i = 0; i < 12; ++i)
+      if (12 * leg + i < 3 * (C.n_apples + C.n_bombs)) prefetch_l2(S.aux + (size_t)(12 * leg + i) * n + e);
   }
   // DRAM -> L2 prefetch of the state a CTA `prefetch_ctas` further on will load (CTAs start roughly in index
   // order): its prologue then waits for an L2 hit instead of a DRAM access.
@@ -284,6 +290,19 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
   const float done_prev = ld_now(S.done + e);
   const float ep_ret = C.track_metrics ? ld_now(S.ep_return + e) : 0.0f;
   const float aux_side = (KIND == POBRAX_ANT_HEAVENHELL) ? ld_now(S.aux + 2 * n + e) : 0.0f;
+  // Tag target / Gather objects: issued here so that their (L2) latency hides behind the observation math
+  float tag_tx = 0.0f, tag_ty = 0.0f;
+  if (KIND == POBRAX_ANT_TAG) { tag_tx = ld_now(S.aux + 2 * n + e); tag_ty = ld_now(S.aux + 3 * n + e); }
+  float obj[4][3];
+  if (KIND == POBRAX_ANT_GATHER) {
+    const int n_obj = C.n_apples + C.n_bombs;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ko = 4 * leg + i;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) obj[i][c] = ko < n_obj ? ld_now(S.aux + (size_t)(3 * ko + c) * n + e) : 0.0f;
+    }
+  }
   __syncwarp();
   stage_common_obs<KIND>(row, r, k, acc, leg, C);
   if (C.auto_reset == POBRAX_AUTORESET_CACHED && done_prev != 0.0f) steps = 0.0f;  // AutoResetWrapper.step head
@@ -324,7 +343,7 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
     // _step_target (ant_tag.py:129-146): rng, rng1 = split(rng); choice = randint(rng1, (), 0, 4)
     const int choice = tag_choice;
     const Key knext = tag_knext;
-    const float tx = S.aux[2 * n + e], ty = S.aux[3 * n + e];
+    const float tx = tag_tx, ty = tag_ty;
     float vx = __fsub_rn(r.T.p.x, tx), vy = __fsub_rn(r.T.p.y, ty);
     const float nv = norm2_rn(vx, vy);
     vx = __fdiv_rn(vx, nv); vy = __fdiv_rn(vy, nv);
@@ -354,15 +373,12 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
     }
   } else {  // POBRAX_ANT_GATHER
     const int n_obj = C.n_apples + C.n_bombs;
-    float obj[4][3], dist[4];
+    float dist[4];
     int caught_a = 0, caught_b = 0, all_wait = 1;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int ko = 4 * leg + i;
       if (ko < n_obj) {
-        obj[i][0] = S.aux[(size_t)(3 * ko) * n + e];
-        obj[i][1] = S.aux[(size_t)(3 * ko + 1) * n + e];
-        obj[i][2] = S.aux[(size_t)(3 * ko + 2) * n + e];
         dist[i] = norm2_rn(__fsub_rn(r.T.p.x, obj[i][0]), __fsub_rn(r.T.p.y, obj[i][1]));
       } else {
         obj[i][0] = obj[i][1] = obj[i][2] = 0.0f; dist[i] = CUDART_INF_F;

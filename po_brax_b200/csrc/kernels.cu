@@ -19,6 +19,9 @@
 
 namespace pobrax {
 
+#ifndef POBRAX_ANT_WARPS_PER_SMSP
+#define POBRAX_ANT_WARPS_PER_SMSP 5
+#endif
 #ifndef POBRAX_WALL_WARPS_PER_SMSP
 #define POBRAX_WALL_WARPS_PER_SMSP 4      // resident warps per SM sub-partition the wall variants are compiled for
 #endif
@@ -33,7 +36,7 @@ template <int KIND> struct StepCfg {
   static constexpr int threads = (KIND == POBRAX_ANT || KIND == POBRAX_ANT_TAG) ? 32 : 64;
 #endif
   static constexpr int envs = threads / 4;
-  static constexpr int min_blocks = (KIND == POBRAX_ANT ? 5 : POBRAX_WALL_WARPS_PER_SMSP) * (128 / threads);  // 96 / 128 registers
+  static constexpr int min_blocks = (KIND == POBRAX_ANT ? POBRAX_ANT_WARPS_PER_SMSP : POBRAX_WALL_WARPS_PER_SMSP) * (128 / threads);  // 96 / 128 registers
 };
 
 // ------------------------------------------------------------------------------------------- helpers

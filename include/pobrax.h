@@ -16,6 +16,7 @@
  *                          envs/ant_tag.py:107-181, brax.envs.ant.Ant.step, i.e. brax.System.step (10 substeps)
  *                          + task logic + brax EpisodeWrapper + brax AutoResetWrapper (envs/wrappers.py:27)
  *   pobrax_reset_where_done  gym-level autoreset, envs/wrappers.py:245-262 (fresh keys, select by done)
+ *   pobrax_reset_where_done_chain  the same, gym key chain (wrappers.py:160-163) on the device: no host sync
  *   pobrax_unpack_qp/pack_qp  State.qp pytree (brax.QP pos/rot/vel/ang [N,nb,*]) <-> packed SoA state
  *   pobrax_split_keys      jax.random.split(key, n) as used by VmapGymWrapper._reset, envs/wrappers.py:160-163
  */
@@ -136,6 +137,11 @@ int pobrax_reset(void* handle, const uint32_t* keys, PobraxState* st, void* stre
 int pobrax_step(void* handle, PobraxState* st, const float* action, void* stream);
 /* gym autoreset: where st->done != 0, replace qp/aux/obs by reset(keys[i]) and zero steps. */
 int pobrax_reset_where_done(void* handle, const uint32_t* keys, PobraxState* st, void* stream);
+/* The same with the gym key chain of VmapGymWrapper._reset (envs/wrappers.py:160-163, 247-248) kept on the device,
+ * so AutoresetVmapGymWrapper.step needs no `done.any()` host round trip: chain = device uint32[4] = {gym key k0, k1,
+ * scratch flag (0 between calls), spare}. If some env is done: keys = split(gym key, N + 1), done envs reset from
+ * keys[i + 1] and gym key <- keys[0]; if none is done nothing changes (the reference draws no keys either). */
+int pobrax_reset_where_done_chain(void* handle, uint32_t* chain, PobraxState* st, void* stream);
 
 /* brax.QP views: pos[N][nb][3], rot[N][nb][4], vel[N][nb][3], ang[N][nb][3] (device). */
 int pobrax_unpack_qp(void* handle, const float* qp, const float* aux, float* pos, float* rot, float* vel,

@@ -62,6 +62,7 @@ EXPORTS = {
     'pobrax_reset': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PobraxState), C.c_void_p]),
     'pobrax_step': (C.c_int, [C.c_void_p, C.POINTER(PobraxState), C.c_void_p, C.c_void_p]),
     'pobrax_reset_where_done': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PobraxState), C.c_void_p]),
+    'pobrax_reset_where_done_chain': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PobraxState), C.c_void_p]),
     'pobrax_unpack_qp': (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),
     'pobrax_pack_qp': (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),
     'pobrax_split_pairs': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

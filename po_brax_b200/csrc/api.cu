@@ -15,7 +15,7 @@
 namespace pobrax {
 cudaError_t launch_step(const DevConst& C, const PobraxState& S, const float* action, cudaStream_t st);
 cudaError_t launch_reset(const DevConst& C, const PobraxState& S, const uint32_t* keys, const float2* grid,
-                         int only_done, cudaStream_t st);
+                         int only_done, uint32_t* chain, cudaStream_t st);
 cudaError_t launch_unpack(const DevConst& C, const float* qp, const float* aux, float* pos, float* rot, float* vel,
                           float* ang, cudaStream_t st);
 cudaError_t launch_pack(const DevConst& C, const float* pos, const float* rot, const float* vel, const float* ang,
@@ -459,7 +459,7 @@ extern "C" int pobrax_reset(void* handle, const uint32_t* keys, PobraxState* st,
   Handle* h = static_cast<Handle*>(handle);
   if (int rc = check_state(h, st, true)) return rc;
   DeviceGuard g(h->device);
-  cudaError_t e = pobrax::launch_reset(h->C, *st, keys, h->grid, 0, static_cast<cudaStream_t>(stream));
+  cudaError_t e = pobrax::launch_reset(h->C, *st, keys, h->grid, 0, nullptr, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? 0 : fail_cuda("pobrax_reset launch", e);
 }
 
@@ -468,8 +468,17 @@ extern "C" int pobrax_reset_where_done(void* handle, const uint32_t* keys, Pobra
   Handle* h = static_cast<Handle*>(handle);
   if (int rc = check_state(h, st, false)) return rc;
   DeviceGuard g(h->device);
-  cudaError_t e = pobrax::launch_reset(h->C, *st, keys, h->grid, 1, static_cast<cudaStream_t>(stream));
+  cudaError_t e = pobrax::launch_reset(h->C, *st, keys, h->grid, 1, nullptr, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? 0 : fail_cuda("pobrax_reset_where_done launch", e);
+}
+
+extern "C" int pobrax_reset_where_done_chain(void* handle, uint32_t* chain, PobraxState* st, void* stream) {
+  if (!handle || !chain) return fail("pobrax_reset_where_done_chain: null argument");
+  Handle* h = static_cast<Handle*>(handle);
+  if (int rc = check_state(h, st, false)) return rc;
+  DeviceGuard g(h->device);
+  cudaError_t e = pobrax::launch_reset(h->C, *st, nullptr, h->grid, 1, chain, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? 0 : fail_cuda("pobrax_reset_where_done_chain launch", e);
 }
 
 extern "C" int pobrax_step(void* handle, PobraxState* st, const float* action, void* stream) {

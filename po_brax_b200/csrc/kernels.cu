@@ -506,7 +506,7 @@ __device__ __forceinline__ void default_leg(Rig& r, const LegK& k, float qh, flo
 template <int KIND>
 __global__ void __launch_bounds__(kThreads, 2)
 reset_kernel(const __grid_constant__ DevConst C, const PobraxState S, const uint32_t* __restrict__ keys,
-             const float2* __restrict__ grid_xy, int only_done) {
+             const float2* __restrict__ grid_xy, int only_done, uint32_t* __restrict__ chain) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int leg = lane & 3, es = lane >> 2;
@@ -520,14 +520,22 @@ reset_kernel(const __grid_constant__ DevConst C, const PobraxState S, const uint
   float* row = stage + es * D;
   uint32_t* sort_keys = reinterpret_cast<uint32_t*>(smem + (size_t)(kThreads / 32) * 8 * D) +
                         (size_t)(warp * 8 + es) * (KIND == POBRAX_ANT_GATHER ? C.n_grid : 0);
+  const bool active = !only_done || S.done[e] != 0.0f;  // uniform over the quad
+  if (only_done && !__any_sync(kFull, active)) return;   // gym autoreset: most warps have no finished env
 #pragma unroll 1
   for (int i = lane; i < 8 * D; i += 32) stage[i] = 0.0f;
   __syncwarp();
-
-  const bool active = !only_done || S.done[e] != 0.0f;  // uniform over the quad
-  if (only_done && !__any_sync(kFull, active)) return;   // gym autoreset: most warps have no finished env
   const LegK k = leg_consts(C, leg);
-  Key key; key.k0 = keys[2 * e]; key.k1 = keys[2 * e + 1];
+  Key key;
+  if (chain) {
+    // gym key chain on the device (VmapGymWrapper._reset, wrappers.py:160-163): env i resets from
+    // split(gym_key, N + 1)[i + 1]; chain[2] tells chain_advance_kernel that keys were drawn.
+    Key gym; gym.k0 = chain[0]; gym.k1 = chain[1];
+    key = split_at(gym, C.n_envs + 1, (int)e + 1);
+    if (active) chain[2] = 1u;
+  } else {
+    key.k0 = keys[2 * e]; key.k1 = keys[2 * e + 1];
+  }
   constexpr int NSPLIT = (KIND == POBRAX_ANT) ? 3 : (KIND == POBRAX_ANT_GATHER ? 4 : 5);
   const Key rng0 = split_at(key, NSPLIT, 0), r1 = split_at(key, NSPLIT, 1), r2 = split_at(key, NSPLIT, 2);
   Key r3 = rng0, r4 = rng0;
@@ -837,9 +845,18 @@ static cudaError_t launch_step_t(const DevConst& C, const PobraxState& S, const 
   return cudaGetLastError();
 }
 
+// gym_key <- split(gym_key, N + 1)[0] if the reset kernel before it drew keys (some env was done)
+__global__ void chain_advance_kernel(uint32_t* chain, int n_envs) {
+  if (chain[2] != 0u) {
+    Key gym; gym.k0 = chain[0]; gym.k1 = chain[1];
+    const Key nxt = split_at(gym, n_envs + 1, 0);
+    chain[0] = nxt.k0; chain[1] = nxt.k1; chain[2] = 0u;
+  }
+}
+
 template <int KIND>
 static cudaError_t launch_reset_t(const DevConst& C, const PobraxState& S, const uint32_t* keys, const float2* grid,
-                                  int only_done, cudaStream_t st) {
+                                  int only_done, uint32_t* chain, cudaStream_t st) {
   size_t smem = obs_stage_bytes(C);
   if (KIND == POBRAX_ANT_GATHER) smem += (size_t)kEnvsPerBlock * C.n_grid * sizeof(uint32_t);
   static bool attr_set = false;
@@ -848,7 +865,8 @@ static cudaError_t launch_reset_t(const DevConst& C, const PobraxState& S, const
     attr_set = true;
   }
   const int blocks = (C.n_envs + kEnvsPerBlock - 1) / kEnvsPerBlock;
-  reset_kernel<KIND><<<blocks, kThreads, smem, st>>>(C, S, keys, grid, only_done);
+  reset_kernel<KIND><<<blocks, kThreads, smem, st>>>(C, S, keys, grid, only_done, chain);
+  if (chain) chain_advance_kernel<<<1, 1, 0, st>>>(chain, C.n_envs);
   return cudaGetLastError();
 }
 
@@ -863,12 +881,12 @@ cudaError_t launch_step(const DevConst& C, const PobraxState& S, const float* ac
 }
 
 cudaError_t launch_reset(const DevConst& C, const PobraxState& S, const uint32_t* keys, const float2* grid,
-                         int only_done, cudaStream_t st) {
+                         int only_done, uint32_t* chain, cudaStream_t st) {
   switch (C.env_kind) {
-    case POBRAX_ANT: return launch_reset_t<POBRAX_ANT>(C, S, keys, grid, only_done, st);
-    case POBRAX_ANT_HEAVENHELL: return launch_reset_t<POBRAX_ANT_HEAVENHELL>(C, S, keys, grid, only_done, st);
-    case POBRAX_ANT_GATHER: return launch_reset_t<POBRAX_ANT_GATHER>(C, S, keys, grid, only_done, st);
-    case POBRAX_ANT_TAG: return launch_reset_t<POBRAX_ANT_TAG>(C, S, keys, grid, only_done, st);
+    case POBRAX_ANT: return launch_reset_t<POBRAX_ANT>(C, S, keys, grid, only_done, chain, st);
+    case POBRAX_ANT_HEAVENHELL: return launch_reset_t<POBRAX_ANT_HEAVENHELL>(C, S, keys, grid, only_done, chain, st);
+    case POBRAX_ANT_GATHER: return launch_reset_t<POBRAX_ANT_GATHER>(C, S, keys, grid, only_done, chain, st);
+    case POBRAX_ANT_TAG: return launch_reset_t<POBRAX_ANT_TAG>(C, S, keys, grid, only_done, chain, st);
   }
   return cudaErrorInvalidValue;
 }

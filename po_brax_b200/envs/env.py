@@ -332,6 +332,19 @@ class Env:
         out._keys = keys
         return out
 
+    def reset_where_done_chain(self, state: State, chain: torch.Tensor) -> State:
+        """reset_where_done with the gym key chain on the device: `chain` = int32[4] tensor (gym key k0, k1, flag = 0,
+        spare). Where some env is done: keys = split(gym key, N + 1), done envs <- reset(keys[i + 1]), gym key <-
+        keys[0] -- what AutoresetVmapGymWrapper.step (wrappers.py:245-262) does, without its host round trip."""
+        if chain.dtype != torch.int32 or chain.numel() != 4 or chain.device != self.device or not chain.is_contiguous():
+            raise ValueError('chain must be a contiguous int32[4] tensor on the env\'s device')
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pobrax_reset_where_done_chain(self._h, chain.data_ptr(), C.byref(state._c()),
+                                                              self._stream()), 'pobrax_reset_where_done_chain')
+        out = State(self, state.buf)
+        out._cstate = state._cstate
+        return out
+
     def split_keys(self, key, n=None, first=0, count=None) -> torch.Tensor:
         """jax.random.split(key, n)[first:first+count] on the device (int32 bit patterns)."""
         n = self.batch_size + 1 if n is None else n

@@ -5,6 +5,7 @@ rewards and dones are torch CUDA tensors (the reference returns device arrays as
 from collections import namedtuple
 from typing import Optional
 
+import numpy as np
 import torch
 
 from .. import random as prandom
@@ -135,16 +136,36 @@ class VmapGymWrapper:
 class AutoresetVmapGymWrapper(VmapGymWrapper):
     """wrappers.py:240-262: when any env is done, draw a fresh batch of keys from the stored gym key and
     reset exactly the done envs (qp/obs replaced, steps zeroed; reward/done/metrics/rng/truncation kept).
-    `sync_free=True` skips the reference's `done.any()` host round trip: keys are then drawn every step."""
 
-    def __init__(self, env: Env, batch_size: int, seed: int = 0, backend: Optional[str] = None, sync_free: bool = False):
+    `sync_free=True` (default): the gym key lives in a 4-word device buffer while stepping and the library makes the
+    "any env done?" decision, the key draw and the key advance on the device (`pobrax_reset_where_done_chain`), so
+    a step is two launches and no host round trip. Keys and results are identical to `sync_free=False`, which
+    follows the reference literally (`done.any()` on the host, keys drawn by a split launch)."""
+
+    def __init__(self, env: Env, batch_size: int, seed: int = 0, backend: Optional[str] = None, sync_free: bool = True):
+        self._chain = None   # int32[4] device tensor (gym key k0, k1, flag, spare) while the key lives on the device
         super().__init__(env, batch_size, seed, backend)
         self.sync_free = sync_free
 
+    @property
+    def _key(self):
+        if self._chain is not None:   # pull the gym key back from the device (one small copy; rare: reset / inspection)
+            v = self._chain[:2].cpu().numpy().view(np.uint32)
+            self._host_key, self._chain = (int(v[0]), int(v[1])), None
+        return self._host_key
+
+    @_key.setter
+    def _key(self, key):
+        self._host_key, self._chain = (int(key[0]), int(key[1])), None
+
     def step(self, action):
-        self._state = self._env.step(self._state, action)
-        s = self._state
-        if self.sync_free or bool(s.done.any()):
+        self._state = s = self._env.step(self._state, action)
+        if self.sync_free:
+            if self._chain is None:
+                words = np.array([self._host_key[0], self._host_key[1], 0, 0], dtype=np.uint32).view(np.int32)
+                self._chain = torch.from_numpy(words).to(self._env.device)
+            self._state = s = self._env.reset_where_done_chain(s, self._chain)
+        elif bool(s.done.any()):
             self._key, keys = self._reset_keys()
             self._state = s = self._env.reset_where_done(s, keys)
         return s.obs, s.reward, s.done, s.metrics

@@ -332,6 +332,36 @@ def test_gym_adapters_follow_the_reference_key_chain():
     assert fresh.obs.shape == (n, 114)
 
 
+@pytest.mark.parametrize('kind', ['ant_tag', 'ant_gather'])
+def test_gym_autoreset_device_key_chain_equals_host_round_trip(kind):
+    """AutoresetVmapGymWrapper.step (wrappers.py:245-262): with the gym key chain on the device
+    (pobrax_reset_where_done_chain, no `done.any()` round trip) every buffer and the stored gym key are bit-identical
+    to the reference-literal host path -- keys are drawn only on steps where some env finished."""
+    from po_brax_b200 import envs
+    n, T = 48, 40
+    a_env = envs.create_gym_env(kind, batch_size=n, seed=5, episode_length=13)
+    b_env = envs.create_gym_env(kind, batch_size=n, seed=5, episode_length=13)
+    assert a_env.sync_free
+    b_env.sync_free = False
+    oa, ob = a_env.reset(), b_env.reset()
+    assert torch.equal(oa, ob)
+    g = torch.Generator(device='cuda').manual_seed(11)
+    draws = 0
+    for t in range(T):
+        act = torch.rand((n, 8), device='cuda', generator=g) * 2 - 1
+        key_before = b_env._key
+        ra, rb = a_env.step(act), b_env.step(act)
+        draws += b_env._key != key_before
+        for x, y in zip(ra[:3], rb[:3]):
+            assert torch.equal(x, y), t
+        sa, sb = a_env._state, b_env._state
+        for name in ('qp', 'aux', 'steps', 'truncation', 'rng'):
+            if sa.buf.get(name) is not None:
+                assert torch.equal(sa.buf[name], sb.buf[name]), (t, name)
+    assert 0 < draws < T            # some steps finished an episode (keys drawn), some did not (gym key untouched)
+    assert a_env._key == b_env._key  # pulled back from the device chain
+
+
 @pytest.mark.parametrize('kind', ['ant_heavenhell', 'ant_tag'])
 def test_randomized_autoreset_naive(kind):
     """wrappers.py:30-80: where done, qp/obs <- reset(info['rng']); Tag's key advances each step, HeavenHell's

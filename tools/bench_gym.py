@@ -1,8 +1,10 @@
-"""Gym-path timing: AutoresetVmapGymWrapper.step (step kernel + done.any() sync + reset_where_done) per step."""
+"""Gym-path timing: AutoresetVmapGymWrapper.step per step -- sync_free=False: step kernel + done.any() host round
+trip + key split + reset_where_done; sync_free=True (default): step kernel + reset_where_done_chain, no host sync.
+    python tools/bench_gym.py [n_envs]"""
 import os, sys, time, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from po_brax_b200 import envs
-n = 1 << 20
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 for sync_free in (False, True):
     e = envs.create_gym_env('ant_heavenhell', batch_size=n, seed=0)
     e.sync_free = sync_free

@@ -310,12 +310,13 @@ class Env:
         state.metrics / state.info in place); the returned State shares them."""
         if not isinstance(action, torch.Tensor):
             action = torch.as_tensor(np.asarray(action, np.float32))
-        action = action.to(device=self.device, dtype=torch.float32).contiguous()
+        if action.device != self.device or action.dtype != torch.float32 or not action.is_contiguous():
+            action = action.to(device=self.device, dtype=torch.float32).contiguous()
         if action.shape != (self.batch_size, self.action_size):
             raise ValueError(f'action must have shape ({self.batch_size}, {self.action_size}), got {tuple(action.shape)}')
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.pobrax_step(self._h, C.byref(state._c()), action.data_ptr(), self._stream()),
-                       'pobrax_step')
+        # no torch.cuda.device() context here: the library selects the handle's device itself (small batches are
+        # bound by this host path, not by the kernel)
+        _lib.check(self.lib.pobrax_step(self._h, C.byref(state._c()), action.data_ptr(), self._stream()), 'pobrax_step')
         out = State(self, state.buf)
         out._cstate = state._cstate
         out._action = action
@@ -338,9 +339,8 @@ class Env:
         keys[0] -- what AutoresetVmapGymWrapper.step (wrappers.py:245-262) does, without its host round trip."""
         if chain.dtype != torch.int32 or chain.numel() != 4 or chain.device != self.device or not chain.is_contiguous():
             raise ValueError('chain must be a contiguous int32[4] tensor on the env\'s device')
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.pobrax_reset_where_done_chain(self._h, chain.data_ptr(), C.byref(state._c()),
-                                                              self._stream()), 'pobrax_reset_where_done_chain')
+        _lib.check(self.lib.pobrax_reset_where_done_chain(self._h, chain.data_ptr(), C.byref(state._c()),
+                                                          self._stream()), 'pobrax_reset_where_done_chain')
         out = State(self, state.buf)
         out._cstate = state._cstate
         return out

@@ -78,6 +78,7 @@ def obs_tolerances(kind, nb, obs_dim):
     atol[tight] = POS_TOL[0]
     rtol[tight] = POS_TOL[1]
     atol[P + 4:P + 12] = 5e-6                     # joint angles (atan2 of unit-vector products)
+    atol[P + 18:P + 26] = 2 * VEL_ATOL            # joint velocities: (w_parent - w_child).axis, two angular velocities
     end = P + 26 + 6 * nb
     atol[end:] = 1e-5                             # task extras (exact unless stated otherwise by the test)
     return atol, rtol

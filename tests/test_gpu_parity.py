@@ -1,5 +1,7 @@
 """CUDA path vs the CPU oracle through the public env API (which calls the C-ABI via ctypes).
 Run on the B200 box: python -m pytest tests -m gpu."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -106,7 +108,16 @@ def _ambiguous_contacts(oenv, qp, eps=1e-5):
 @pytest.mark.parametrize('kind', KINDS)
 def test_step_teacher_forced(kind):
     """One env step from identical states, T times along an oracle rollout (BASELINE config 1 key scheme)."""
-    n, T = 128, 25
+    _teacher_forced(kind, 128, 25)
+
+
+def test_step_teacher_forced_long_heavenhell():
+    """BASELINE config 1 (Ant-HeavenHell, 128 envs, random-action rollout), teacher-forced deeper into the episode
+    (ants against walls, fallen ants, finished envs); POBRAX_LONG_T=1000 runs the full length (~2 min of oracle)."""
+    _teacher_forced('ant_heavenhell', 128, int(os.environ.get('POBRAX_LONG_T', '120')))
+
+
+def _teacher_forced(kind, n, T):
     keys = P.keys_for(n, seed=0)
     oenv = oenvs.ENVS[kind]()
     nb = oenv.sys.num_bodies

@@ -226,7 +226,7 @@ __device__ __forceinline__ void quad_sum2(V3& a, V3& b) {
 //          A box separated from the segment's bounding box by >= rad along some axis cannot touch: skipped
 //          exactly.
 //  m == 0: the torso's ground-plane candidate (sphere vs z = 0).
-__device__ __noinline__ Imp rare_group(V3 p, V3 e, V3 v, V3 w, float rad, float reach2, float inv_m, unsigned m,
+__device__ __noinline__ Imp rare_group(V3 p, V3 e, V3 v, V3 w, float rad, float inv_m, unsigned m,
                                        const float4* __restrict__ walls, float baumgarte, float friction,
                                        float elasticity) {
   const V3 zero = mk(0.f, 0.f, 0.f);
@@ -257,9 +257,8 @@ __device__ __noinline__ Imp rare_group(V3 p, V3 e, V3 v, V3 w, float rad, float 
   return o;
 }
 
-__device__ __forceinline__ Imp wall_group(const Body& b, V3 e, float rad, float reach, float inv_m, unsigned m,
-                                          const DevConst& C) {
-  return rare_group(b.p, e, b.v, b.w, rad, reach * reach, inv_m, m, C.walls, C.baumgarte, C.friction, C.elasticity);
+__device__ __forceinline__ Imp wall_group(const Body& b, V3 e, float rad, float inv_m, unsigned m, const DevConst& C) {
+  return rare_group(b.p, e, b.v, b.w, rad, inv_m, m, C.walls, C.baumgarte, C.friction, C.elasticity);
 }
 
 // Inline fast path of a body's Arena group for the common case -- ONE candidate box and the closest segment point
@@ -423,25 +422,25 @@ __device__ __forceinline__ void contacts2(Rig2& r, const DevConst& C, V3 dA, V3 
       Imp t;
       t.dv = t.dw = zero;
       if (hitT)
-        t = rare_group(r.T.p, zero, r.T.v, r.T.w, C.r_torso, 0.0f, C.inv_m_torso, 0u, C.walls, C.baumgarte, C.friction,
+        t = rare_group(r.T.p, zero, r.T.v, r.T.w, C.r_torso, C.inv_m_torso, 0u, C.walls, C.baumgarte, C.friction,
                        C.elasticity);
       if (WALLS && mT != 0u) {
         // torso and Aux near a wall are rare (the lower legs reach furthest): no inline fast path, one code copy
-        const Imp c = wall_group(r.T, zero, C.r_torso, C.r_torso + 1e-4f, C.inv_m_torso, mT, C);
+        const Imp c = wall_group(r.T, zero, C.r_torso, C.inv_m_torso, mT, C);
         t.dv += c.dv; t.dw += c.dw;
       }
       r.T.v += t.dv; r.T.w += t.dw;
       if (leg == 0) { row_add(acc.cv, 0, t.dv); row_add(acc.ca, 0, t.dw); }
     }
     if (WALLS && mA != 0u) {
-      const Imp c = wall_group(A, C.s_aux * dA, C.r_leg, C.seg_aux + C.r_leg + 1e-4f, C.inv_m_leg, mA, C);
+      const Imp c = wall_group(A, C.s_aux * dA, C.r_leg, C.inv_m_leg, mA, C);
       A.v += c.dv; A.w += c.dw;
       row_add(acc.cv, 1 + 2 * leg, c.dv); row_add(acc.ca, 1 + 2 * leg, c.dw);
     }
     if (WALLS && mB != 0u) {
       Imp c;
       if (!wall_single(B, C.s_foot * dB, C.r_leg, C.inv_m_leg, mB, C, c))
-        c = wall_group(B, C.s_foot * dB, C.r_leg, C.seg_foot + C.r_leg + 1e-4f, C.inv_m_leg, mB, C);
+        c = wall_group(B, C.s_foot * dB, C.r_leg, C.inv_m_leg, mB, C);
       B.v += c.dv; B.w += c.dw;
       acc.Bv += c.dv; acc.Bw += c.dw;
     }

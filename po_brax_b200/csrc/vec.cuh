@@ -11,9 +11,7 @@ __host__ __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b
 __host__ __device__ __forceinline__ V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
 __host__ __device__ __forceinline__ V3 operator*(float s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
 __host__ __device__ __forceinline__ V3 operator*(V3 a, float s) { return mk(s * a.x, s * a.y, s * a.z); }
-__host__ __device__ __forceinline__ V3 operator*(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
 __host__ __device__ __forceinline__ V3& operator+=(V3& a, V3 b) { a.x += b.x; a.y += b.y; a.z += b.z; return a; }
-__host__ __device__ __forceinline__ V3& operator-=(V3& a, V3 b) { a.x -= b.x; a.y -= b.y; a.z -= b.z; return a; }
 // s*a + b as three FMAs
 __host__ __device__ __forceinline__ V3 fma3(float s, V3 a, V3 b) { return mk(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)); }
 __host__ __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
@@ -23,8 +21,6 @@ __host__ __device__ __forceinline__ V3 cross(V3 a, V3 b) {
 
 // One rigid body of brax.QP: pos, rot (w,x,y,z), vel, ang.
 struct Body { V3 p; float qw, qx, qy, qz; V3 v, w; };
-// Columns of the rotation matrix of a body.
-struct Frame { V3 c0, c1, c2; };
 
 // ---- packed float32x2 (Blackwell FFMA2 / FADD2 / FMUL2: one issue slot for two float32 lanes) -------------
 // A pair lives in an aligned 64-bit register pair (lo, hi). ptxas folds negation (pk(-lo, -hi)), scalar broadcast

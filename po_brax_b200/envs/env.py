@@ -202,6 +202,10 @@ class Env:
             pop2('priest_position', p.priest_xy)
             if 'visible_radius' in kw:
                 p.visible_radius = float(kw.pop('visible_radius'))
+            if 'init_ant_pos' in kw:  # test hook: ant_heavenhell.py:73 self._init_ant_pos = [[lo_x, lo_y], [hi_x, hi_y]]
+                ip = kw.pop('init_ant_pos')
+                p.init_lo[0], p.init_lo[1], p.init_hi[0], p.init_hi[1] = (float(ip[0][0]), float(ip[0][1]),
+                                                                          float(ip[1][0]), float(ip[1][1]))
             hw = 2.0  # ant_heavenhell.py:63 hallway_width
             xs = [p.heaven_hell_xy[0][0], p.heaven_hell_xy[1][0], p.priest_xy[0]]
             ys = [p.heaven_hell_xy[0][1], p.heaven_hell_xy[1][1], p.priest_xy[1]]

@@ -27,14 +27,17 @@ def create_fn(env_name: str, **kwargs) -> Callable[..., Env]:
 def create_gym_env(env_name: str, batch_size: Optional[int] = None, seed: int = 0, backend: Optional[str] = None,
                    **kwargs):
     """__init__.py:98-121: autoreset and statistics move to the gym layer."""
-    from .wrappers import AutoresetVmapGymWrapper, EvalGymWrapper
+    from .wrappers import AutoresetGymWrapper, AutoresetVmapGymWrapper, EvalGymWrapper
     kwargs['auto_reset'] = False
     eval_metrics = kwargs.pop('eval_metrics', False)
     discount = kwargs.pop('discount', 1.)
     if batch_size is not None and batch_size <= 0:
         raise ValueError('`batch_size` should either be None or a positive integer.')
     environment = create(env_name=env_name, batch_size=batch_size, **kwargs)
-    e = AutoresetVmapGymWrapper(environment, environment.batch_size, seed=seed, backend=backend)
+    if batch_size is None:
+        e = AutoresetGymWrapper(environment, seed=seed, backend=backend)
+    else:
+        e = AutoresetVmapGymWrapper(environment, batch_size, seed=seed, backend=backend)
     if eval_metrics:
         e = EvalGymWrapper(e, discount=discount)
     return e

@@ -171,6 +171,53 @@ class AutoresetVmapGymWrapper(VmapGymWrapper):
         return s.obs, s.reward, s.done, s.metrics
 
 
+class AutoresetGymWrapper:
+    """wrappers.py:232-237 over brax's GymWrapper: the UNBATCHED gym.Env view (create_gym_env(batch_size=None)).
+    reset: key1, key2 = split(key); state = env.reset(key2); key <- key1 (brax GymWrapper.reset). step: when the
+    episode ends the env is reset in full from the key chain (fresh info['rng'] too, unlike the batched adapter)
+    and the RESET observation is returned together with the finished step's reward / done (`obs` is rebound by the
+    reset in the reference). The fused env is batched, so this wraps a batch of one and
+    strips the batch axis; `if done` is a host decision in the reference too."""
+
+    def __init__(self, env: Env, seed: int = 0, backend: Optional[str] = None):
+        if env.batch_size != 1:
+            raise ValueError('AutoresetGymWrapper wraps an unbatched env (create(..., batch_size=None))')
+        self._env = env
+        self.metadata = {'render.modes': ['human', 'rgb_array'],
+                         'video.frames_per_second': 1 / (env.params.dt * env.params.action_repeat)}
+        self.seed(seed)
+        self.backend = backend
+        self._state = None
+        inf = float('inf')
+        self.observation_space = Box(-inf, inf, (env.observation_size,), 'float32')
+        self.action_space = Box(-1.0, 1.0, (env.action_size,), 'float32')
+
+    def seed(self, seed: int = 0):
+        self._key = prandom.prng_key(seed)
+
+    def _reset(self):
+        key1, key2 = prandom.split_at(self._key, 2, 0), prandom.split_at(self._key, 2, 1)
+        self._state = self._env.reset(np.array([key2], dtype=np.uint32))
+        self._key = key1
+        return self._state.obs[0]
+
+    def reset(self):
+        return self._reset()
+
+    def step(self, action):
+        if not isinstance(action, torch.Tensor):
+            action = torch.as_tensor(np.asarray(action, np.float32))
+        self._state = s = self._env.step(self._state, action.reshape(1, -1))
+        obs, reward, done, info = s.obs[0], s.reward[0].clone(), s.done[0].clone(), {k: v[0].clone() for k, v in s.metrics.items()}
+        if bool(done):
+            obs = self._reset()
+        return obs, reward, done, info
+
+    @property
+    def unwrapped(self):
+        return self._env
+
+
 class EvalGymWrapper:
     """wrappers.py:175-229: running episode statistics (returns, discounted returns, lengths). The reference
     appends finished episodes to Python lists and reports their nanmean; here the same means are kept as

@@ -580,3 +580,31 @@ def test_constructor_kwargs_of_the_reference_envs(kind, kw):
             mask[:, -2 * oenv.n_bins:] &= _gather_reading_mask(oenv, nxt, got)
         P.assert_obs_close(P.t2n(got.obs), nxt.obs, kind, nb, f'{kind} kwargs t={t}', mask=mask)
         s = nxt
+
+
+def test_unbatched_gym_env_follows_the_brax_gym_key_chain():
+    """create_gym_env(batch_size=None) -> AutoresetGymWrapper (wrappers.py:232-237 over brax GymWrapper): reset draws
+    key1, key2 = split(key), resets from key2 and keeps key1; a finished episode triggers a FULL reset from the chain
+    (fresh info['rng']) whose observation is returned with the finished step's reward / done."""
+    from po_brax_b200 import envs
+    e = envs.create_gym_env('ant_tag', seed=7, episode_length=4)
+    oenv = oenvs.AntTagEnv()
+    obs = e.reset()
+    ks = tf.split(tf.prng_key(7), 2)
+    want = oenv.reset(ks[1:2])
+    assert tuple(obs.shape) == (103,) and e.observation_space.shape == (103,) and e.action_space.shape == (8,)
+    cols = list(range(29)) + [101, 102]   # everything but the contact columns (resting-foot sign ambiguity)
+    assert np.allclose(P.t2n(obs)[cols], want.obs[0, cols], atol=2e-5)
+    assert list(e._key) == ks[0].tolist()
+    for t in range(4):
+        o, r, d, info = e.step(np.zeros(8, np.float32))
+        assert o.shape == (103,) and r.dim() == 0 and d.dim() == 0 and set(info) == {'hits'}
+        assert bool(d) == (t == 3)            # truncated by episode_length 4 (no tag, no death from rest)
+    ks2 = tf.split(ks[0], 2)
+    want2 = oenv.reset(ks2[1:2])
+    assert np.allclose(P.t2n(o)[cols], want2.obs[0, cols], atol=2e-5)
+    assert (P.rng_bits(e._state.info['rng']) == want2.info['rng']).all()   # full reset: fresh info['rng']
+    assert list(e._key) == ks2[0].tolist()
+    assert float(e._state.info['steps'][0]) == 0.0 and float(e._state.done[0]) == 0.0
+    with pytest.raises(ValueError):
+        envs.create_gym_env('ant_tag', batch_size=0)

@@ -76,3 +76,17 @@ def test_host_threefry_matches_oracle():
         for j in (0, 1, 4, 8):
             assert list(prandom.split_at(k, 9, j)) == full[j].tolist()
     assert prandom.threefry2x32((0x13198a2e, 0x03707344), 0x243f6a88, 0x85a308d3) == (0xc4923a9c, 0x483df7a0)
+
+
+def test_bench_flop_figure_is_not_inflated():
+    """bench.py's roofline uses SURVEY 8(d)'s specialised count (4.30e4 FLOPs per env-step). The oracle's own
+    System.step, run on operation-counting arrays (oracle/count_ops.py), is the as-written upper bound: the bench figure
+    must not exceed it, and the structural counts must hold (8 joints x 10 substeps = 80 atan2)."""
+    import bench
+    from oracle import count_ops
+    c = count_ops.count_step('ant', n=2)
+    total = count_ops.flops(c)
+    assert c['atan2'] == 80 and not any(k.startswith('other:') for k in c)
+    assert bench.FLOPS_PER_ENV_STEP['ant'] <= total <= 1.5 * bench.FLOPS_PER_ENV_STEP['ant']
+    hh = count_ops.flops(count_ops.count_step('ant_heavenhell', walls=False, n=2))
+    assert bench.FLOPS_PER_ENV_STEP['ant_heavenhell'] <= hh

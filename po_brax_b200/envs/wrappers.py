@@ -142,30 +142,66 @@ class AutoresetVmapGymWrapper(VmapGymWrapper):
     a step is two launches and no host round trip. Keys and results are identical to `sync_free=False`, which
     follows the reference literally (`done.any()` on the host, keys drawn by a split launch)."""
 
-    def __init__(self, env: Env, batch_size: int, seed: int = 0, backend: Optional[str] = None, sync_free: bool = True):
+    def __init__(self, env: Env, batch_size: int, seed: int = 0, backend: Optional[str] = None, sync_free: bool = True,
+                 cuda_graph: bool = False):
         self._chain = None   # int32[4] device tensor (gym key k0, k1, flag, spare) while the key lives on the device
+        self._graph = None   # captured (step + reset_where_done_chain) of the current State's buffers
         super().__init__(env, batch_size, seed, backend)
         self.sync_free = sync_free
+        self.cuda_graph = cuda_graph
 
     @property
     def _key(self):
         if self._chain is not None:   # pull the gym key back from the device (one small copy; rare: reset / inspection)
             v = self._chain[:2].cpu().numpy().view(np.uint32)
-            self._host_key, self._chain = (int(v[0]), int(v[1])), None
+            self._host_key, self._chain, self._graph = (int(v[0]), int(v[1])), None, None
         return self._host_key
 
     @_key.setter
     def _key(self, key):
-        self._host_key, self._chain = (int(key[0]), int(key[1])), None
+        self._host_key, self._chain, self._graph = (int(key[0]), int(key[1])), None, None
+
+    def reset(self):
+        self._graph = None   # a reset allocates a new State: the captured launches point at the old buffers
+        return super().reset()
+
+    def _capture(self):
+        """cuda_graph=True: the gym step (fused env step + device-side autoreset with the key chain, three launches)
+        is captured once per State into a CUDA graph and replayed, so a step costs one graph launch on the host.
+        Small batches are bound by the host path, not by the kernels. Results are identical:
+        the same launches on the same buffers. The library's lazy per-kernel setup runs on a scratch state first
+        (nothing but kernel launches may happen while capturing)."""
+        env = self._env
+        scratch = env.reset(env.split_keys((0, 0), self.num_envs + 1, first=1, count=self.num_envs))
+        scratch = env.step(scratch, torch.zeros((self.num_envs, env.action_size), device=env.device))
+        env.reset_where_done_chain(scratch, torch.zeros(4, dtype=torch.int32, device=env.device))
+        self._act = torch.zeros((self.num_envs, env.action_size), dtype=torch.float32, device=env.device)
+        torch.cuda.current_stream(env.device).synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            s = env.step(self._state, self._act)
+            self._graph_state = env.reset_where_done_chain(s, self._chain)
+        self._graph = g
 
     def step(self, action):
-        self._state = s = self._env.step(self._state, action)
         if self.sync_free:
             if self._chain is None:
                 words = np.array([self._host_key[0], self._host_key[1], 0, 0], dtype=np.uint32).view(np.int32)
                 self._chain = torch.from_numpy(words).to(self._env.device)
+            if self.cuda_graph:
+                if self._graph is None:
+                    self._capture()
+                if not isinstance(action, torch.Tensor):
+                    action = torch.as_tensor(np.asarray(action, np.float32))
+                self._act.copy_(action.reshape(self._act.shape), non_blocking=True)
+                self._graph.replay()
+                self._state = s = self._graph_state
+                return s.obs, s.reward, s.done, s.metrics
+            self._state = s = self._env.step(self._state, action)
             self._state = s = self._env.reset_where_done_chain(s, self._chain)
-        elif bool(s.done.any()):
+            return s.obs, s.reward, s.done, s.metrics
+        self._state = s = self._env.step(self._state, action)
+        if bool(s.done.any()):
             self._key, keys = self._reset_keys()
             self._state = s = self._env.reset_where_done(s, keys)
         return s.obs, s.reward, s.done, s.metrics

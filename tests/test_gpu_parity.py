@@ -608,3 +608,32 @@ def test_unbatched_gym_env_follows_the_brax_gym_key_chain():
     assert float(e._state.info['steps'][0]) == 0.0 and float(e._state.done[0]) == 0.0
     with pytest.raises(ValueError):
         envs.create_gym_env('ant_tag', batch_size=0)
+
+
+@pytest.mark.parametrize('kind', ['ant_tag', 'ant_heavenhell'])
+def test_gym_step_as_cuda_graph_equals_plain_launches(kind):
+    """create_gym_env(..., cuda_graph=True) replays (step + device-side autoreset) as one CUDA graph: every output of
+    every step, the State and the gym key chain must equal the plain launches bit for bit, across resets (a reset
+    re-captures) and with actions given as host arrays."""
+    from po_brax_b200 import envs
+    n = 300
+    g = torch.Generator(device='cuda').manual_seed(11)
+    acts = torch.rand((45, n, 8), device='cuda', generator=g) * 2 - 1
+    outs = []
+    for graph in (False, True):
+        e = envs.create_gym_env(kind, batch_size=n, seed=5, episode_length=7, cuda_graph=graph)
+        rec = [e.reset().clone()]
+        for t in range(45):
+            if t == 20:
+                rec.append(e.reset().clone())           # new State buffers: the graph path must re-capture
+            a = acts[t] if t % 2 else acts[t].cpu().numpy()
+            o, r, d, info = e.step(a)
+            rec += [o.clone(), r.clone(), d.clone()] + [v.clone() for v in info.values()]
+        rec += [v.clone() for v in e._state.buf.values() if v is not None]
+        assert (e._graph is not None) == graph
+        rec.append(torch.tensor(list(e._key)))          # pulls the key chain back to the host (drops the graph)
+        torch.cuda.synchronize()
+        outs.append(rec)
+    assert len(outs[0]) == len(outs[1])
+    for i, (a, b) in enumerate(zip(*outs)):
+        assert torch.equal(a, b), (kind, i)

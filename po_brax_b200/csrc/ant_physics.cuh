@@ -261,6 +261,45 @@ __device__ __forceinline__ Imp wall_group(const Body& b, V3 e, float rad, float 
   return rare_group(b.p, e, b.v, b.w, rad, inv_m, m, C.walls, C.baumgarte, C.friction, C.elasticity);
 }
 
+// Exact early-out of a body's Arena group with ONE candidate box k: the segment's bounding box is separated from
+// the box by more than rad along some axis, so they cannot touch (the out-of-line group culls with the same gap).
+__device__ __forceinline__ bool box_out_of_reach(const Body& b, V3 e, float rad, V3 lo, V3 hi) {
+  const float ex = fabsf(e.x), ey = fabsf(e.y), ez = fabsf(e.z), rs = rad + 1e-5f;
+  const float gap = fmaxf(fmaxf(fmaxf(lo.x - (b.p.x + ex), (b.p.x - ex) - hi.x), fmaxf(lo.y - (b.p.y + ey), (b.p.y - ey) - hi.y)),
+                          fmaxf(lo.z - (b.p.z + ez), (b.p.z - ez) - hi.z));
+  return gap > rs;
+}
+// The same as a guard in front of the out-of-line group (torso, Aux): true = single candidate and out of reach.
+// An ant that lingers near a wall keeps these bodies flagged for many steps without touching; the guard costs the
+// flagged lane ~20 instructions instead of the group's call + loop + global box loads.
+__device__ __forceinline__ bool wall_far_single(const Body& b, V3 e, float rad, unsigned m, const DevConst& C) {
+  if (m & (m - 1u)) return false;
+  const int k = __ffs(m) - 1;
+  const float4 l4 = C.wall_box[k][0], h4 = C.wall_box[k][1];
+  return box_out_of_reach(b, e, rad, mk(l4.x, l4.y, l4.z), mk(h4.x, h4.y, h4.z));
+}
+
+// A multi-candidate mask (cells near a corner) reduced to the boxes that are exactly within reach: ants that the
+// walls funnel into corners keep two candidates for many steps, but a leg is rarely within reach of both, so
+// the survivor usually takes the single-box inline path (converged with the warp's other flagged lanes) instead of
+// the out-of-line group. Out of line itself: multi-candidate lanes are rare, the loop must not grow the substep.
+__device__ __noinline__ unsigned cull_multi(V3 p, V3 e, float rad, unsigned m, const float4* __restrict__ walls) {
+  unsigned keep = 0u;
+  const float ex = fabsf(e.x), ey = fabsf(e.y), ez = fabsf(e.z), rs = rad + 1e-5f;
+  do {
+    const int k = __ffs(m) - 1;
+    m &= m - 1u;
+    const float4 lo = __ldg(walls + 2 * k), hi = __ldg(walls + 2 * k + 1);
+    const float gap = fmaxf(fmaxf(fmaxf(lo.x - (p.x + ex), (p.x - ex) - hi.x), fmaxf(lo.y - (p.y + ey), (p.y - ey) - hi.y)),
+                            fmaxf(lo.z - (p.z + ez), (p.z - ez) - hi.z));
+    if (!(gap > rs)) keep |= 1u << k;
+  } while (m);
+  return keep;
+}
+__device__ __forceinline__ unsigned cull_candidates(const Body& b, V3 e, float rad, unsigned m, const DevConst& C) {
+  return (m & (m - 1u)) ? cull_multi(b.p, e, rad, m, C.walls) : m;
+}
+
 // Inline fast path of a body's Arena group for the common case -- ONE candidate box and the closest segment point
 // at an end (g(0) >= 0 or g(1) <= 0 in seg_box_t, i.e. no bisection): same arithmetic as contact_general, but
 // from the constant bank and without the call. Returns false when the out-of-line group has to run instead.
@@ -272,12 +311,7 @@ __device__ __forceinline__ bool wall_single(const Body& b, V3 e, float rad, floa
   const V3 lo = mk(l4.x, l4.y, l4.z), hi = mk(h4.x, h4.y, h4.z);
   c.dv = c.dw = mk(0.f, 0.f, 0.f);
   c.hit = 0.0f;
-  {  // exact early-out: the segment's bounding box is separated from the box by > rad along some axis
-    const float ex = fabsf(e.x), ey = fabsf(e.y), ez = fabsf(e.z), rs = rad + 1e-5f;
-    const float gap = fmaxf(fmaxf(fmaxf(lo.x - (b.p.x + ex), (b.p.x - ex) - hi.x), fmaxf(lo.y - (b.p.y + ey), (b.p.y - ey) - hi.y)),
-                            fmaxf(lo.z - (b.p.z + ez), (b.p.z - ez) - hi.z));
-    if (gap > rs) return true;
-  }
+  if (box_out_of_reach(b, e, rad, lo, hi)) return true;
   const V3 a = b.p + e;
   const V3 d = (b.p - e) - a;
   const V3 p1 = a + d;  // g(1) is evaluated at a + 1*d, as in seg_box_t
@@ -424,25 +458,29 @@ __device__ __forceinline__ void contacts2(Rig2& r, const DevConst& C, V3 dA, V3 
       if (hitT)
         t = rare_group(r.T.p, zero, r.T.v, r.T.w, C.r_torso, C.inv_m_torso, 0u, C.walls, C.baumgarte, C.friction,
                        C.elasticity);
-      if (WALLS && mT != 0u) {
-        // torso and Aux near a wall are rare (the lower legs reach furthest): no inline fast path, one code copy
+      if (WALLS && mT != 0u && !wall_far_single(r.T, zero, C.r_torso, mT, C)) {
+        // torso and Aux in wall contact are rare (the lower legs reach furthest): no inline narrow phase, one code
+        // copy out of line behind the inline out-of-reach guard
         const Imp c = wall_group(r.T, zero, C.r_torso, C.inv_m_torso, mT, C);
         t.dv += c.dv; t.dw += c.dw;
       }
       r.T.v += t.dv; r.T.w += t.dw;
       if (leg == 0) { row_add(acc.cv, 0, t.dv); row_add(acc.ca, 0, t.dw); }
     }
-    if (WALLS && mA != 0u) {
+    if (WALLS && mA != 0u && !wall_far_single(A, C.s_aux * dA, C.r_leg, mA, C)) {
       const Imp c = wall_group(A, C.s_aux * dA, C.r_leg, C.inv_m_leg, mA, C);
       A.v += c.dv; A.w += c.dw;
       row_add(acc.cv, 1 + 2 * leg, c.dv); row_add(acc.ca, 1 + 2 * leg, c.dw);
     }
     if (WALLS && mB != 0u) {
-      Imp c;
-      if (!wall_single(B, C.s_foot * dB, C.r_leg, C.inv_m_leg, mB, C, c))
-        c = wall_group(B, C.s_foot * dB, C.r_leg, C.inv_m_leg, mB, C);
-      B.v += c.dv; B.w += c.dw;
-      acc.Bv += c.dv; acc.Bw += c.dw;
+      const unsigned m = cull_candidates(B, C.s_foot * dB, C.r_leg, mB, C);
+      if (m != 0u) {
+        Imp c;
+        if (!wall_single(B, C.s_foot * dB, C.r_leg, C.inv_m_leg, m, C, c))
+          c = wall_group(B, C.s_foot * dB, C.r_leg, C.inv_m_leg, m, C);
+        B.v += c.dv; B.w += c.dw;
+        acc.Bv += c.dv; acc.Bw += c.dw;
+      }
     }
   }
   B.v += gv; B.w += gw;

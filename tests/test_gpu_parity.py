@@ -117,15 +117,29 @@ def test_step_teacher_forced_long_heavenhell():
     _teacher_forced('ant_heavenhell', 128, int(os.environ.get('POBRAX_LONG_T', '120')))
 
 
-def _teacher_forced(kind, n, T):
+def test_step_teacher_forced_corner_walls():
+    """HeavenHell ants spawned around the staircase corner of the T junction (wall boxes x in [2, 3] up to y = 5.5 and
+    y in [5, 6] from x = 2.5): two candidate walls per cell, Aux / torso wall contacts, closest points inside the
+    segment (bisection) -- the out-of-line wall groups and the multi-candidate cull against the oracle."""
+    st = _teacher_forced('ant_heavenhell', 128, 40, init_box=((1.3, 4.9), (2.0, 5.9)), min_clear=0.5)
+    assert st['aux_wall_contacts'] > 20 and st['torso_contacts'] > 0, st   # the scenario does reach those colliders
+
+
+def _teacher_forced(kind, n, T, init_box=None, min_clear=0.75):
     keys = P.keys_for(n, seed=0)
     oenv = oenvs.ENVS[kind]()
     nb = oenv.sys.num_bodies
+    kw = {}
+    if init_box is not None:   # ant_heavenhell.py:73 self._init_ant_pos
+        oenv._init_lo, oenv._init_hi = np.array(init_box[0], np.float32), np.array(init_box[1], np.float32)
+        kw['init_ant_pos'] = init_box
     s = oenv.reset(keys)
-    env = _make(kind, n, auto_reset=False, episode_length=1000)
+    env = _make(kind, n, auto_reset=False, episode_length=1000, **kw)
     rng = tf.prng_key(1)
     oenv.sys.track_margin = True
     compared = []
+    stats = {'aux_wall_contacts': 0, 'torso_contacts': 0}
+    Pc = 1 if kind == 'ant' else 3
     for t in range(T):
         rng, a = P.actions_for(rng, n)
         cs = env.state_from_qp(P.qp_to_torch(s.qp), rng=s.info.get('rng'))
@@ -138,6 +152,9 @@ def _teacher_forced(kind, n, T):
         # other branch under any other float32 evaluation order: they get a loose bound, the rest the tight one.
         clear = oenv.sys.margin > P.BRANCH_MARGIN
         compared.append(clear.mean())
+        cvel = nxt.obs[:, Pc + 26:Pc + 26 + 3 * nb].reshape(n, nb, 3)   # clip(contact.vel): Aux bodies only touch walls
+        stats['aux_wall_contacts'] += int((np.abs(cvel[:, [1, 3, 5, 7]]).sum(-1) > 0).sum())
+        stats['torso_contacts'] += int((np.abs(cvel[:, 0]).sum(-1) > 0).sum())
         P.assert_qp_close(got.qp, nxt.qp, f'{kind} t={t}', rows=clear)
         P.assert_qp_close(got.qp, nxt.qp, f'{kind} t={t} (ambiguous envs)', rows=~clear, loose=True)
         assert np.array_equal(P.t2n(got.done), np.asarray(nxt.done, np.float32)), f'{kind} t={t} done'
@@ -161,7 +178,9 @@ def _teacher_forced(kind, n, T):
             mask[:, -2 * oenv.n_bins:] &= _gather_reading_mask(oenv, nxt, got)
         P.assert_obs_close(P.t2n(got.obs), nxt.obs, kind, nb, f'{kind} t={t}', mask=mask)
         s = nxt
-    assert np.mean(compared) > 0.75, compared
+    assert np.mean(compared) > min_clear, compared
+    stats['clear'] = float(np.mean(compared))
+    return stats
 
 
 def _gather_reading_mask(oenv, nxt, got):

@@ -115,7 +115,7 @@ def main_reference(args):
         'e2e': {'value': val, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -325,7 +325,7 @@ def main_graft(args):
         'episode_metrics': dict(zip(('episodes', 'sum_return', 'sum_length', 'truncations', 'hits', 'heavens', 'hells',
                                      'dead_steps'), acc)),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -335,6 +335,18 @@ def env_obs(name):
     return {'ant': 87, 'ant_heavenhell': 114, 'ant_tag': 103, 'ant_gather': 211}[name]
 
 
+def emit(line):
+    """The ONE JSON line of the contract, written to the real stdout (see __main__)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == '__main__':
     a = parse()
+    # Libraries write to stdout on their own (NCCL prints "NCCL version ..." there when NCCL_DEBUG is set on the box):
+    # fd 1 is pointed at stderr for the whole run and the JSON line goes to a saved copy of the real stdout.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     sys.exit(main_reference(a) if a.impl == 'reference' else main_graft(a))

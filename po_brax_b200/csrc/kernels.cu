@@ -33,7 +33,7 @@ template <int KIND> struct StepCfg {
 #ifdef POBRAX_TUNE_THREADS   // tuning builds: one CTA size for every family
   static constexpr int threads = POBRAX_TUNE_THREADS;
 #else
-  static constexpr int threads = (KIND == POBRAX_ANT || KIND == POBRAX_ANT_TAG) ? 32 : 64;
+  static constexpr int threads = KIND == POBRAX_ANT_GATHER ? 64 : 32;   // re-swept after the steady-state wall-path change
 #endif
   static constexpr int envs = threads / 4;
   static constexpr int min_blocks = (KIND == POBRAX_ANT ? POBRAX_ANT_WARPS_PER_SMSP : POBRAX_WALL_WARPS_PER_SMSP) * (128 / threads);  // 96 / 128 registers

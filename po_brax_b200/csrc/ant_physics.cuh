@@ -167,13 +167,13 @@ __device__ __forceinline__ Imp contact_general(V3 p, V3 e, V3 v, V3 w, float rad
 
 // Candidate walls of a body centred at (x, y): bit w of the byte set <=> wall w is within that body type's
 // reach of the table cell (exact rectangle-rectangle distance in xy, so culling stays exact). One table per
-// body type `kind` (0 torso sphere, 1 Aux capsule, 2 lower-leg capsule); outside the table: every wall.
+// body type `kind` (0 torso sphere, 1 Aux capsule, 2 lower-leg capsule), read through a layered 2D texture:
+// cell = floor((p - origin) / cell_size) is one FMA per axis here, and the texture unit does the float -> cell
+// conversion, the clamp onto the border cells (which list every wall, as does everything outside the table) and the
+// addressing -- 3 instructions per lookup instead of 10 (30 lookups per lane and step).
 __device__ __forceinline__ unsigned wall_mask_at(const DevConst& C, int kind, float x, float y) {
-  // cell = (p - origin) / cell_size, one FMA per axis; the unsigned min sends negatives (and NaN -> 0) to a border
-  // cell, and border cells list every wall.
-  const unsigned ix = min((unsigned)(int)fmaf(x, C.sdf_inv_cell, C.sdf_bx), (unsigned)(C.sdf_nx - 1));
-  const unsigned iy = min((unsigned)(int)fmaf(y, C.sdf_inv_cell, C.sdf_by), (unsigned)(C.sdf_ny - 1));
-  return __ldg(C.wall_mask + (unsigned)(kind * C.sdf_plane) + iy * (unsigned)C.sdf_nx + ix);
+  return tex2DLayered<unsigned char>((cudaTextureObject_t)C.wall_tex, fmaf(x, C.sdf_inv_cell, C.sdf_bx),
+                                     fmaf(y, C.sdf_inv_cell, C.sdf_by), kind);
 }
 
 // Per-lane constants of leg l.

@@ -27,7 +27,8 @@ cudaError_t launch_split_pairs(const uint32_t* keys, int n, uint32_t* a, uint32_
 struct Handle {
   DevConst C;
   int device;
-  uint8_t* sdf = nullptr;  // wall candidate mask tables
+  cudaArray_t sdf_array = nullptr;       // wall candidate mask tables: layered 2D array behind a texture object
+  cudaTextureObject_t sdf_tex = 0;
   float4* walls = nullptr;
   float2* grid = nullptr;
 };
@@ -328,7 +329,8 @@ static int build_dev_const(const PobraxParams* p, DevConst* Cp, std::vector<uint
     const int nx = (int)std::ceil((x1 - x0) / cell), ny = (int)std::ceil((y1 - y0) / cell);
     if (nx <= 2 || ny <= 2 || (long long)nx * ny > (1 << 22)) return fail("wall extent unsupported (mask table too large)");
     // Bit w of a cell (per body type): some point of the cell is within that body's reach (capsule half
-    // segment + radius, plus slack for the float cell lookup) of wall w in the xy-plane. Border cells (and
+    // segment + radius, plus 2 mm of slack for the cell lookup: float rounding of the coordinate, and a texture
+    // unit that may quantise the coordinate to 1/256 of a 125 mm cell before flooring) of wall w in the xy-plane. Border cells (and
     // everything outside the table, which clamps onto them) list every wall.
     const uint8_t all = (uint8_t)((1u << C.n_walls) - 1u);
     const size_t plane = (size_t)nx * ny;
@@ -349,7 +351,7 @@ static int build_dev_const(const PobraxParams* p, DevConst* Cp, std::vector<uint
         }
     C.sdf_x0 = (float)x0; C.sdf_y0 = (float)y0; C.sdf_inv_cell = (float)(1.0 / cell);
     C.sdf_bx = (float)(-x0 / cell); C.sdf_by = (float)(-y0 / cell);
-    C.sdf_nx = nx; C.sdf_ny = ny; C.sdf_plane = (int)plane;
+    C.sdf_nx = nx; C.sdf_ny = ny;
   }
   // ---- task
   C.dying_cost = p->dying_cost; C.visible_radius = p->visible_radius;
@@ -401,19 +403,39 @@ extern "C" int pobrax_create(const PobraxParams* p, int device, void** handle) {
   if (prop.major < 10) { cudaSetDevice(prev); return fail("pobrax_create: kernels are built for sm_100a (B200) only"); }
   Handle* h = new Handle();
   h->device = device;
-  if (!sdf.empty()) {
-    if ((e = cudaMalloc(&h->sdf, sdf.size())) != cudaSuccess) { delete h; cudaSetDevice(prev); return fail_cuda("cudaMalloc(sdf)", e); }
-    cudaMemcpy(h->sdf, sdf.data(), sdf.size(), cudaMemcpyHostToDevice);
-  }
   if (!grid.empty()) {
-    if ((e = cudaMalloc(&h->grid, grid.size() * sizeof(float2))) != cudaSuccess) { cudaFree(h->sdf); delete h; cudaSetDevice(prev); return fail_cuda("cudaMalloc(grid)", e); }
+    if ((e = cudaMalloc(&h->grid, grid.size() * sizeof(float2))) != cudaSuccess) { delete h; cudaSetDevice(prev); return fail_cuda("cudaMalloc(grid)", e); }
     cudaMemcpy(h->grid, grid.data(), grid.size() * sizeof(float2), cudaMemcpyHostToDevice);
   }
   if (!walls.empty()) {
-    if ((e = cudaMalloc(&h->walls, walls.size() * sizeof(float4))) != cudaSuccess) { cudaFree(h->sdf); cudaFree(h->grid); delete h; cudaSetDevice(prev); return fail_cuda("cudaMalloc(walls)", e); }
+    if ((e = cudaMalloc(&h->walls, walls.size() * sizeof(float4))) != cudaSuccess) { cudaFree(h->grid); delete h; cudaSetDevice(prev); return fail_cuda("cudaMalloc(walls)", e); }
     cudaMemcpy(h->walls, walls.data(), walls.size() * sizeof(float4), cudaMemcpyHostToDevice);
   }
-  C.wall_mask = h->sdf;
+  if (!sdf.empty()) {  // layered 2D texture over the three tables (point sampling, clamp, unnormalised coordinates)
+    cudaChannelFormatDesc fmt = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+    cudaExtent ext = make_cudaExtent((size_t)C.sdf_nx, (size_t)C.sdf_ny, 3);
+    if ((e = cudaMalloc3DArray(&h->sdf_array, &fmt, ext, cudaArrayLayered)) != cudaSuccess) {
+      cudaSetDevice(prev); pobrax_destroy(h); return fail_cuda("cudaMalloc3DArray(wall masks)", e);
+    }
+    cudaMemcpy3DParms cp = {};
+    cp.srcPtr = make_cudaPitchedPtr(sdf.data(), (size_t)C.sdf_nx, (size_t)C.sdf_nx, (size_t)C.sdf_ny);
+    cp.dstArray = h->sdf_array;
+    cp.extent = ext;
+    cp.kind = cudaMemcpyHostToDevice;
+    if ((e = cudaMemcpy3D(&cp)) != cudaSuccess) { cudaSetDevice(prev); pobrax_destroy(h); return fail_cuda("cudaMemcpy3D(wall masks)", e); }
+    cudaResourceDesc res = {};
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = h->sdf_array;
+    cudaTextureDesc td = {};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    if ((e = cudaCreateTextureObject(&h->sdf_tex, &res, &td, nullptr)) != cudaSuccess) {
+      cudaSetDevice(prev); pobrax_destroy(h); return fail_cuda("cudaCreateTextureObject(wall masks)", e);
+    }
+    C.wall_tex = (unsigned long long)h->sdf_tex;
+  }
   C.walls = h->walls;
   h->C = C;
   cudaSetDevice(prev);
@@ -427,7 +449,8 @@ extern "C" int pobrax_destroy(void* handle) {
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(h->device);
-  if (h->sdf) cudaFree(h->sdf);
+  if (h->sdf_tex) cudaDestroyTextureObject(h->sdf_tex);
+  if (h->sdf_array) cudaFreeArray(h->sdf_array);
   if (h->walls) cudaFree(h->walls);
   if (h->grid) cudaFree(h->grid);
   cudaSetDevice(prev);

@@ -53,8 +53,9 @@ struct DevConst {
   // walls: axis-aligned boxes in world coordinates + a per-cell candidate mask for exact culling
   const float4* walls;                       // device float4[n_walls][2]: (lo.xyz, -), (hi.xyz, -)
   float4 wall_box[kMaxWalls][2];             // the same boxes in the constant bank (inline fast path)
-  const uint8_t* wall_mask;                  // [3 body types][sdf_ny][sdf_nx] candidate-wall bit mask of each xy cell
-  int32_t sdf_plane;                         // sdf_nx * sdf_ny
+  unsigned long long wall_tex;               // cudaTextureObject_t: [3 body types][sdf_ny][sdf_nx] candidate-wall bit
+                                             // mask of each xy cell as a layered 2D texture (point sampling, clamped,
+                                             // unnormalised coordinates)
   float sdf_x0, sdf_y0, sdf_inv_cell, sdf_bx, sdf_by;   // sdf_bx = -x0 * inv_cell (cell = fma(p, inv_cell, b))
   int32_t sdf_nx, sdf_ny;
   // task

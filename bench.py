@@ -4,7 +4,7 @@
     python bench.py --gpus 1 --steps 200 --warmup 20
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...      # the restated CPU oracle on all host cores (same metric)
+    python bench.py --impl reference ...      # the restated CPU oracle (C step, all host cores; same metric)
 
 One "step" = one fused env.step over the whole batch (physics x10 substeps + task logic + obs +
 episode/autoreset). Envs shard across GPUs with no data-path collective (weak scaling: envs per GPU
@@ -40,15 +40,20 @@ def parse():
     ap.add_argument('--e2e-steps', type=int, default=20)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--ref-envs-per-core', type=int, default=32)
+    ap.add_argument('--ref-envs-per-core', type=int, default=2048)
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------ CPU (oracle) arm
+CPU_KIND = ('restated CPU oracle, not reference JAX: oracle/brax_step.c (scalar C restatement of the brax v1 step, '
+            'gcc -O3, one process per core) under the NumPy task / episode / autoreset logic of oracle/envs.py')
+
+
 def _ref_worker(conn, env_name, m, seed):
     import numpy as np
-    from oracle import envs as oenvs, threefry as tf
+    from oracle import cstep, envs as oenvs, threefry as tf
     env = oenvs.create(env_name, episode_length=1000, auto_reset=True)
+    cstep.attach(env.env.sys, threads=1)
     keys = tf.split(tf.prng_key(seed), m + 1)[1:]
     s = env.reset(keys)
     rng = np.random.default_rng(seed)
@@ -63,8 +68,10 @@ def _ref_worker(conn, env_name, m, seed):
 
 
 def run_cpu_oracle(env_name, steps, warmup, m, procs):
-    """Times the restated CPU oracle (oracle/, NumPy float32) on `procs` processes x `m` envs each."""
+    """Times the restated CPU oracle (oracle/: C float32 step + NumPy env logic) on `procs` processes x `m` envs."""
     import multiprocessing as mp
+    from oracle import cstep
+    cstep.build()   # before the fork: the workers only dlopen it
     ctx = mp.get_context('fork')
     pipes, ps = [], []
     for i in range(procs):
@@ -104,7 +111,7 @@ def main_reference(args):
     steps = max(1, min(args.steps, 200))
     warmup = max(1, min(args.warmup, 5))
     val, dt = run_cpu_oracle(args.env, steps, warmup, m, cores)
-    sample = f'{cores} processes x {m} envs x {steps} steps of {args.env} (restated NumPy oracle, not reference JAX)'
+    sample = f'{cores} processes x {m} envs x {steps} steps of {args.env}, {dt:.1f} s ({CPU_KIND})'
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
         'steps': steps, 'warmup': warmup, 'ms_per_step': 1e3 * dt / steps, 'higher_is_better': True,
@@ -307,10 +314,10 @@ def main_graft(args):
     }
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        m, st_ = 64, 200
-        v, dt = run_cpu_oracle(args.env, st_, 2, m, 1)
-        cpu_baseline = {'value': v, 'unit': 'env-steps/s', 'cores': 1, 'kind': 'port',
-                        'sample': f'1 process x {m} envs x {st_} steps of {args.env} (restated NumPy oracle), {dt:.1f} s'}
+        cores, m, st_ = os.cpu_count() or 1, args.ref_envs_per_core, 100
+        v, dt = run_cpu_oracle(args.env, st_, 3, m, cores)
+        cpu_baseline = {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
+                        'sample': f'{cores} processes x {m} envs x {st_} steps of {args.env}, {dt:.1f} s ({CPU_KIND})'}
     line = {
         'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',

@@ -22,9 +22,12 @@ def _uniform_np(rng, n, lo, hi):
     return np.random.default_rng(rng).uniform(lo, hi, n)
 
 
-def _replay(dtype):
+def _replay(dtype, c_step=False):
     cfg = json.load(open(os.path.join(HERE, 'golden', 'ant_tag_config.json')))
     sys_ = bx.System(cfg, dtype=dtype, walls=False)  # that revision's Arena: capsule walls at +-7, never reached
+    if c_step:  # the scalar C restatement (oracle/brax_step.c) replays the same fixture
+        from oracle import cstep
+        cstep.attach(sys_, threads=1)
     rng = np.random.default_rng(0).integers(0, 2 ** 32, dtype=np.uint32, size=2)
     assert rng.tolist() == [3653403231, 2735729615]
     ks = _split_np(rng, 5)
@@ -42,10 +45,11 @@ def _replay(dtype):
     return frames
 
 
+@pytest.mark.parametrize('c_step', [False, True], ids=['numpy', 'c'])
 @pytest.mark.parametrize('dtype,tol0,tol1,tol20', [(np.float64, 1e-7, 2e-6, 3e-5), (np.float32, 1e-6, 2e-6, 3e-5)])
-def test_golden_rollout(dtype, tol0, tol1, tol20):
+def test_golden_rollout(dtype, tol0, tol1, tol20, c_step):
     gold = np.load(os.path.join(HERE, 'golden', 'ant_tag_rollout.npz'))
-    frames = _replay(dtype)
+    frames = _replay(dtype, c_step)
     errs = []
     for t, (pos, rot) in enumerate(frames):
         e = max(np.abs(pos[:9] - gold['pos'][t, :9]).max(), np.abs(rot[:9] - gold['rot'][t, :9]).max())

@@ -62,7 +62,7 @@ static inline void FN(quat_mul)(const REAL *u, const REAL *v, REAL *o) {
 
 /* brax_v1.System._impulse for one contact of body b; adds nothing, returns dvel/dang of this contact. */
 static inline void FN(impulse)(const FN(SysDesc) *S, int b, const REAL *bpos, const REAL *cpos, const REAL *cvel,
-                               const REAL *n, REAL pen, REAL *dvel, REAL *dang) {
+                               const REAL *n, REAL pen, REAL *dvel, REAL *dang, double *mg) {
     const REAL one = 1, zero = 0;
     REAL mass = S->mass[b]; const REAL *ii = S->inv_inertia + 3 * b;
     REAL inv_m = one / mass;
@@ -89,6 +89,17 @@ static inline void FN(impulse)(const FN(SysDesc) *S, int b, const REAL *bpos, co
     REAL an = (pen > zero && nv < zero && J > zero) ? one : zero;
     REAL ad = an * (nd > (REAL)0.01 ? one : zero);
     for (int i = 0; i < 3; i++) { dvel[i] = pn_v[i] * an + pd_v[i] * ad; dang[i] = pn_a[i] * an + pd_a[i] * ad; }
+    if (mg) {   /* brax_v1.System._note_margin: distance to the nearest discontinuous branch (test aid) */
+        double m = fabs((double)pen) * 100.0;
+        if (pen > zero) {
+            m = fmin(m, fabs((double)nv));
+            if (nv < zero) {
+                m = fmin(m, fabs((double)J));
+                if (J > zero) m = fmin(m, fabs((double)nd - 0.01));
+            }
+        }
+        *mg = fmin(*mg, m);
+    }
 }
 
 /* g(t) of brax_v1.System._closest_segment_box */
@@ -125,7 +136,7 @@ static void FN(closest_segment_box)(const REAL *a, const REAL *b, const REAL *lo
 
 /* brax_v1.System._contacts on one env: cv/ca [nb][3] = ground group + wall group */
 static void FN(contacts)(const FN(SysDesc) *S, const REAL *pos, const REAL *rot, const REAL *vel, const REAL *ang,
-                         REAL *cv, REAL *ca) {
+                         REAL *cv, REAL *ca, double *mg) {
     const int nb = S->nb;
     REAL cnt[MAXB], sv[MAXB][3], sa[MAXB][3];
     for (int b = 0; b < nb; b++) for (int i = 0; i < 3; i++) { cv[3 * b + i] = 0; ca[3 * b + i] = 0; }
@@ -144,7 +155,7 @@ static void FN(contacts)(const FN(SysDesc) *S, const REAL *pos, const REAL *rot,
             FN(cross3)(ang + 3 * b, r, w);
             for (int i = 0; i < 3; i++) { cvel[i] = vel[3 * b + i] + w[i]; gp[i] = pos[3 * g + i] - cpos[i]; }
             REAL pen = FN(dot3)(gp, n);
-            FN(impulse)(S, b, p, cpos, cvel, n, pen, dv, da);
+            FN(impulse)(S, b, p, cpos, cvel, n, pen, dv, da, mg);
             cnt[b] += (dv[0] != 0 || dv[1] != 0 || dv[2] != 0) ? (REAL)1 : (REAL)0;
             for (int i = 0; i < 3; i++) { sv[b][i] += dv[i]; sa[b][i] += da[i]; }
         }
@@ -186,7 +197,7 @@ static void FN(contacts)(const FN(SysDesc) *S, const REAL *pos, const REAL *rot,
                 REAL pen = rad - dist;
                 FN(cross3)(ang + 3 * b, r, w);
                 for (int i = 0; i < 3; i++) cvel[i] = vel[3 * b + i] + w[i];
-                FN(impulse)(S, b, p, bp, cvel, n, pen, dv, da);
+                FN(impulse)(S, b, p, bp, cvel, n, pen, dv, da, mg);
                 cnt[b] += (dv[0] != 0 || dv[1] != 0 || dv[2] != 0) ? (REAL)1 : (REAL)0;
                 for (int i = 0; i < 3; i++) { sv[b][i] += dv[i]; sa[b][i] += da[i]; }
                 any = 1;
@@ -201,7 +212,7 @@ static void FN(contacts)(const FN(SysDesc) *S, const REAL *pos, const REAL *rot,
 
 /* brax_v1.System.substep on one env, in place; cvel/cang = this substep's contact impulses */
 static void FN(substep)(const FN(SysDesc) *S, REAL *pos, REAL *rot, REAL *vel, REAL *ang, const REAL *act,
-                        REAL *cvel, REAL *cang) {
+                        REAL *cvel, REAL *cang, double *mg) {
     const int nb = S->nb, nj = S->nj;
     const REAL h = S->h;
     /* kinetic */
@@ -250,6 +261,8 @@ static void FN(substep)(const FN(SysDesc) *S, REAL *pos, REAL *rot, REAL *vel, R
         REAL lo = S->j_limit[2 * j], hi = S->j_limit[2 * j + 1];
         REAL da = psi[j] < lo ? lo - psi[j] : (REAL)0;
         if (psi[j] > hi) da = hi - psi[j];
+        if (mg)   /* the actuator switches off discontinuously at the joint limits (brax_v1._joints_and_actuators) */
+            *mg = fmin(*mg, fmin(fabs((double)(REAL)(psi[j] - lo)), fabs((double)(REAL)(psi[j] - hi))) * 100.0);
         for (int i = 0; i < 3; i++) {
             REAL t = S->j_stiff[j] * tq[i];
             t = t - S->j_lstr[j] * axis_p[j][i] * da;
@@ -284,7 +297,7 @@ static void FN(substep)(const FN(SysDesc) *S, REAL *pos, REAL *rot, REAL *vel, R
         }
     }
     /* contacts -> collision */
-    FN(contacts)(S, pos, rot, vel, ang, cvel, cang);
+    FN(contacts)(S, pos, rot, vel, ang, cvel, cang, mg);
     for (int b = 0; b < nb; b++) {
         REAL m = S->active[b];
         for (int i = 0; i < 3; i++) {
@@ -294,10 +307,11 @@ static void FN(substep)(const FN(SysDesc) *S, REAL *pos, REAL *rot, REAL *vel, R
     }
 }
 
-/* System.step on N envs in place (QP arrays [N][nb][3|4], act [N][na]); cv/ca [N][nb][3] = summed contact impulses.
+/* System.step on N envs in place (QP arrays [N][nb][3|4], act [N][na]); cv/ca [N][nb][3] = summed contact impulses;
+ * margin [N] (may be NULL) = the env's distance from its nearest discontinuous branch in this step (_note_margin).
  * threads <= 0: OpenMP default. Returns 0, or -1 if the system exceeds the static limits. */
 int FN(brax_step)(const FN(SysDesc) *S, long N, REAL *pos, REAL *rot, REAL *vel, REAL *ang, const REAL *act,
-                  REAL *cv, REAL *ca, int threads) {
+                  REAL *cv, REAL *ca, double *margin, int threads) {
     if (S->nb > MAXB || S->nj > MAXJ || S->na > MAXJ) return -1;
     const int nb = S->nb;
 #ifdef _OPENMP
@@ -309,8 +323,10 @@ int FN(brax_step)(const FN(SysDesc) *S, long N, REAL *pos, REAL *rot, REAL *vel,
         REAL *p = pos + e * nb * 3, *q = rot + e * nb * 4, *v = vel + e * nb * 3, *w = ang + e * nb * 3;
         REAL *ocv = cv + e * nb * 3, *oca = ca + e * nb * 3;
         for (int i = 0; i < 3 * nb; i++) { ocv[i] = 0; oca[i] = 0; }
+        double *mg = margin ? margin + e : 0;
+        if (mg) *mg = 1e9;
         for (int s = 0; s < S->substeps; s++) {
-            FN(substep)(S, p, q, v, w, act + e * S->na, dv, da);
+            FN(substep)(S, p, q, v, w, act + e * S->na, dv, da, mg);
             for (int i = 0; i < 3 * nb; i++) { ocv[i] = ocv[i] + dv[i]; oca[i] = oca[i] + da[i]; }
         }
     }
@@ -327,7 +343,7 @@ int FN(brax_info)(const FN(SysDesc) *S, long N, const REAL *pos, const REAL *rot
 #pragma omp parallel for schedule(static) num_threads(threads)
 #endif
     for (long e = 0; e < N; e++)
-        FN(contacts)(S, pos + e * nb * 3, rot + e * nb * 4, vel + e * nb * 3, ang + e * nb * 3, cv + e * nb * 3, ca + e * nb * 3);
+        FN(contacts)(S, pos + e * nb * 3, rot + e * nb * 4, vel + e * nb * 3, ang + e * nb * 3, cv + e * nb * 3, ca + e * nb * 3, 0);
     return 0;
 }
 

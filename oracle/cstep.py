@@ -59,7 +59,7 @@ class CBackend:
     """Flat description of a brax_v1.System for the C step; keeps the arrays it points to alive."""
 
     def __init__(self, system: bx.System, threads: int = 1):
-        s = system
+        s = self.system = system
         self.dtype = np.dtype(s.dtype)
         if self.dtype == np.float32:
             real, self.sfx = C.c_float, '_f32'
@@ -113,10 +113,14 @@ class CBackend:
         n = pos.shape[0]
         assert pos.shape == (n, self.nb, 3) and rot.shape == (n, self.nb, 4) and act.shape == (n, self.na)
         cv, ca = np.empty_like(pos), np.empty_like(pos)
+        mg = np.empty(n, np.float64) if self.system.track_margin else None
         rc = self._step(C.byref(self.desc), C.c_long(n), *[C.c_void_p(x.ctypes.data) for x in
-                                                           (pos, rot, vel, ang, act, cv, ca)], C.c_int(self.threads))
+                                                           (pos, rot, vel, ang, act, cv, ca)],
+                        C.c_void_p(mg.ctypes.data if mg is not None else None), C.c_int(self.threads))
         if rc:
             raise RuntimeError(f'brax_step{self.sfx} failed: {rc}')
+        if mg is not None:   # same protocol as the NumPy text: the caller clears system.margin before a step
+            self.system.margin = mg if self.system.margin is None else np.minimum(self.system.margin, mg)
         return bx.QP(pos, rot, vel, ang), bx.Info(cv, ca)
 
     def info(self, qp: bx.QP):

@@ -125,9 +125,21 @@ def test_step_teacher_forced_corner_walls():
     assert st['aux_wall_contacts'] > 20 and st['torso_contacts'] > 0, st   # the scenario does reach those colliders
 
 
-def _teacher_forced(kind, n, T, init_box=None, min_clear=0.75):
+@pytest.mark.parametrize('kind,n,T', [('ant', 4096, 6), ('ant_gather', 16384, 4), ('ant_tag', 65536, 3),
+                                      ('ant_heavenhell', 131072, 3)])
+def test_step_teacher_forced_at_baseline_sizes(kind, n, T):
+    """BASELINE configs 2-4 at their full batch sizes and config 5 at its 8-GPU shard size (1 Mi / 8), teacher-forced
+    against the scalar C twin of the oracle (oracle/brax_step.c on all host cores; tests/test_oracle_c.py pins it to
+    the NumPy text and to the golden rollout) under the NumPy task logic: every env of the batch is compared."""
+    _teacher_forced(kind, n, T, c_step=True)   # >= 75 % of the envs are held to the tight gates (HeavenHell: 77 %)
+
+
+def _teacher_forced(kind, n, T, init_box=None, min_clear=0.75, c_step=False):
     keys = P.keys_for(n, seed=0)
     oenv = oenvs.ENVS[kind]()
+    if c_step:
+        from oracle import cstep
+        cstep.attach(oenv.sys, threads=os.cpu_count() or 1)
     nb = oenv.sys.num_bodies
     kw = {}
     if init_box is not None:   # ant_heavenhell.py:73 self._init_ant_pos
@@ -167,7 +179,10 @@ def _teacher_forced(kind, n, T, init_box=None, min_clear=0.75):
             assert (P.rng_bits(got.info['rng']) == nxt.info['rng']).all()
             assert np.array_equal(P.t2n(got.metrics['hits']), nxt.metrics['hits'])
             # the opponent moves along (ant - target)/|ant - target| of the post-physics ant: float tolerance
-            assert np.abs(P.t2n(got.qp.pos)[:, oenv.target_idx] - nxt.qp.pos[:, oenv.target_idx]).max() <= 1e-5
+            # (tight where the ant's own step is unambiguous; an env that took the other contact branch moves its
+            # opponent along a slightly different direction)
+            dtgt = np.abs(P.t2n(got.qp.pos)[:, oenv.target_idx] - nxt.qp.pos[:, oenv.target_idx]).max(axis=-1)
+            assert dtgt[clear].max() <= 1e-5 and dtgt.max() <= P.LOOSE_POS, (dtgt[clear].max(), dtgt.max())
         if kind == 'ant_gather':
             assert np.array_equal(P.t2n(got.metrics['apples']), nxt.metrics['apples'].astype(np.float32))
             assert np.array_equal(P.t2n(got.metrics['bombs']), nxt.metrics['bombs'].astype(np.float32))

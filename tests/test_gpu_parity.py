@@ -233,6 +233,56 @@ def test_free_running_20_steps(kind):
     assert np.median(err) <= 1e-5
 
 
+@pytest.mark.parametrize('kind,n,T', [('ant_heavenhell', 4096, 400), ('ant_tag', 4096, 300), ('ant_gather', 2048, 300),
+                                      ('ant', 2048, 300)])
+def test_free_running_rollout_statistics(kind, n, T):
+    """Past ~100 steps a float32 rollout is chaotic, so env-by-env comparison is meaningless -- but the two
+    implementations must still sample the same process. Free-running create(...) envs (Episode + cached AutoReset)
+    on identical keys and actions for T steps, CUDA vs the C twin of the oracle under the NumPy task logic: the
+    per-env totals of reward, finished episodes and (HeavenHell) each outcome, and the final torso height, must have
+    equal means within 5 standard errors of a two-sample test (conservative: the samples are positively correlated)."""
+    from oracle import cstep
+    keys = P.keys_for(n, seed=5)
+    oenv = oenvs.create(kind)
+    cstep.attach(oenv.env.sys, threads=os.cpu_count() or 1)
+    env = _make(kind, n)
+    s, cs = oenv.reset(keys), env.reset(keys)
+    names = ['reward', 'done'] + (['heaven', 'hell', 'dead'] if kind == 'ant_heavenhell' else [])
+
+    def cats(r, d, xp):
+        out = [r, d]
+        if kind == 'ant_heavenhell':
+            out += [(r == 1).astype(np.float32) if xp is np else (r == 1).float(),
+                    (r == -1).astype(np.float32) if xp is np else (r == -1).float(),
+                    (r == -2).astype(np.float32) if xp is np else (r == -2).float()]
+        return out
+
+    tot_o = [np.zeros(n, np.float64) for _ in names]
+    tot_g = [torch.zeros(n, dtype=torch.float64, device='cuda') for _ in names]
+    rng = tf.prng_key(2)
+    for t in range(T):
+        rng, a = P.actions_for(rng, n)
+        s = oenv.step(s, a)
+        cs = env.step(cs, torch.as_tensor(a, device='cuda'))
+        for acc, v in zip(tot_o, cats(np.asarray(s.reward, np.float32), np.asarray(s.done, np.float32), np)):
+            acc += v
+        for acc, v in zip(tot_g, cats(cs.reward, cs.done.float(), torch)):
+            acc += v
+        if t == 19:   # still in the deterministic regime: the same envs have finished an episode
+            assert (P.t2n(tot_g[1]) != tot_o[1]).sum() <= n // 1000
+    rows = {k: (P.t2n(g), o) for k, g, o in zip(names, tot_g, tot_o)}
+    rows['torso_z'] = (P.t2n(cs.qp.pos)[:, 0, 2].astype(np.float64), s.qp.pos[:, 0, 2].astype(np.float64))
+    report = {}
+    for k, (g, o) in rows.items():
+        assert np.isfinite(g).all() and np.isfinite(o).all(), k
+        se = np.sqrt((g.var() + o.var()) / n)
+        report[k] = (float(g.mean()), float(o.mean()), float(se))
+        assert abs(g.mean() - o.mean()) <= 5 * se + 1e-6, (kind, k, report[k])
+    if kind == 'ant_heavenhell':
+        assert report['done'][0] > 0.02, report   # the rollout is long enough to finish episodes (7.6 % of the envs)
+    print(kind, report)
+
+
 @pytest.mark.parametrize('kind', KINDS)
 def test_episode_and_cached_autoreset(kind):
     """brax EpisodeWrapper + AutoResetWrapper semantics fused into the step kernel (create(auto_reset=True))."""

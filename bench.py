@@ -324,6 +324,8 @@ def main_graft(args):
         'data': 'synthetic',
         'config': {'workload': f'{args.env} (BASELINE configs[4]), {n} envs per GPU, episode_length 1000, cached autoreset, '
                                f'i.i.d. U(-1,1) actions (device-resident, period {period})',
+                   'phase': f'timed steps are steps {W}..{W + K} after a reset of all envs; the cost of a step grows with the '
+                            'time since reset as random-action ants gather along the walls (DESIGN.md section 6)',
                    'envs_per_gpu': n, 'total_envs': total, 'parallelism': f'env-sharded x{world}, no per-step collective',
                    'l2': f'state+obs per GPU = {n * (512 + 4 * env_obs(args.env)) / 1e6:.0f} MB >> 126 MB L2 (inputs larger than L2)',
                    'metric_allreduce_every': 100},

@@ -1,0 +1,107 @@
+"""The DEVICE physics source (po_brax_b200/csrc/ant_physics.cuh: advance2 / substep2 / contacts2, the packed
+float32x2 arithmetic, wall candidate tables, out-of-line contact groups) compiled for the host by g++ and run
+against the oracle -- no GPU (tests/host_emu/emu.cpp explains how the quad shuffles, the texture lookup and the
+PTX are stood in for). It checks the TEXT of what the step kernels run; the parity tests proper are the `-m gpu`
+ones, which run the real kernels through the C ABI.
+
+Same gates as the GPU teacher-forced tests (tests/_parity.py): pos / rot 1e-6 + 2e-6|x|, vel / ang / contact impulses
+3e-4, on the envs whose contact / actuator decisions are not rounding-ambiguous in that step; the loose bound on
+the rest."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import envs as oenvs
+from po_brax_b200 import _lib
+from tests import _parity as P
+from tests import host_emu
+
+KINDS = {'ant': _lib.ANT, 'ant_heavenhell': _lib.ANT_HEAVENHELL, 'ant_tag': _lib.ANT_TAG, 'ant_gather': _lib.ANT_GATHER}
+
+
+class Emu:
+    def __init__(self, kind, **params):
+        self.lib = host_emu.load()
+        p = _lib.PobraxParams()
+        assert _lib.load().pobrax_default_params(KINDS[kind], C.byref(p)) == 0   # host code of the product library
+        p.num_envs = 1
+        for k, v in params.items():
+            setattr(p, k, v)
+        self.h = C.c_void_p()
+        rc = self.lib.emu_create(C.byref(p), C.byref(self.h))
+        assert rc == 0, self.lib.pobrax_last_error()
+        self.nb = self.lib.emu_num_bodies(self.h)
+
+    def step(self, qp, act):
+        a = [np.ascontiguousarray(x, np.float32).copy() for x in (qp.pos, qp.rot, qp.vel, qp.ang)]
+        act = np.ascontiguousarray(act, np.float32)
+        n = a[0].shape[0]
+        assert a[0].shape == (n, self.nb, 3) and act.shape == (n, 8)
+        cv, ca = np.zeros_like(a[0]), np.zeros_like(a[0])
+        ptr = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
+        rc = self.lib.emu_step(self.h, C.c_long(n), *[ptr(x) for x in a], ptr(act), ptr(cv), ptr(ca))
+        assert rc == 0, rc
+        return a, cv, ca
+
+    def __del__(self):
+        if getattr(self, 'h', None):
+            self.lib.emu_destroy(self.h)
+
+
+def _check(kind, oenv, emu, s, T, n, min_clear=0.75, seed=1):
+    from oracle import threefry as tf
+    oenv.sys.track_margin = True
+    rng = tf.prng_key(seed)
+    clear_frac, wall_hits = [], 0
+    for t in range(T):
+        rng, act = P.actions_for(rng, n)
+        oenv.sys.margin = None
+        qp1, info = oenv.sys.step(s.qp, act)
+        (pos, rot, vel, ang), cv, ca = emu.step(s.qp, act)
+        clear = oenv.sys.margin > P.BRANCH_MARGIN
+        clear_frac.append(clear.mean())
+        ant = slice(0, 9)
+        for name, got, want, tight in (('pos', pos, qp1.pos, True), ('rot', rot, qp1.rot, True),
+                                       ('vel', vel, qp1.vel, False), ('ang', ang, qp1.ang, False),
+                                       ('contact.vel', cv, info.contact_vel, False),
+                                       ('contact.ang', ca, info.contact_ang, False)):
+            g, w = got[:, ant], want[:, ant]
+            d = np.abs(g - w)
+            tol = (P.POS_TOL[0] + P.POS_TOL[1] * np.abs(w)) if tight else P.VEL_ATOL
+            assert (d[clear] <= (tol[clear] if tight else tol)).all(), (kind, t, name, d[clear].max())
+            assert (d[~clear] <= (P.LOOSE_POS if tight else P.LOOSE_VEL)).all(), (kind, t, name, 'ambiguous', d[~clear].max())
+        # frozen bodies are not part of the device state: untouched
+        assert np.array_equal(pos[:, 9:], s.qp.pos[:, 9:])
+        wall_hits += int((np.abs(info.contact_vel[:, [1, 3, 5, 7]]).sum(-1) > 0).sum())   # Aux bodies only touch walls
+        s = s.replace(qp=qp1)
+    assert np.mean(clear_frac) > min_clear, clear_frac
+    return wall_hits
+
+
+@pytest.mark.parametrize('kind', list(KINDS))
+def test_device_substep_text_matches_oracle(kind):
+    n, T = 48, 12
+    oenv = oenvs.ENVS[kind]()
+    s = oenv.reset(P.keys_for(n, seed=0))
+    _check(kind, oenv, Emu(kind), s, T, n)
+
+
+def test_device_wall_paths_match_oracle_at_the_corner():
+    """HeavenHell ants spawned around the staircase corner of the T junction (as in the GPU corner test): cells
+    with two candidate walls, Aux wall contacts, closest points inside the segment -- the out-of-line groups."""
+    n, T = 64, 30
+    box = ((1.3, 4.9), (2.0, 5.9))
+    oenv = oenvs.ENVS['ant_heavenhell']()
+    oenv._init_lo, oenv._init_hi = np.array(box[0], np.float32), np.array(box[1], np.float32)
+    s = oenv.reset(P.keys_for(n, seed=0))
+    hits = _check('ant_heavenhell', oenv, Emu('ant_heavenhell'), s, T, n, min_clear=0.5)
+    assert hits > 10, hits
+
+
+def test_action_repeat_runs_more_substeps():
+    """ActionRepeatWrapper (wrappers.py:16-24): dt and substeps scale, h stays."""
+    n = 16
+    oenv = oenvs.ENVS['ant'](action_repeat=2)
+    s = oenv.reset(P.keys_for(n, seed=2))
+    _check('ant', oenv, Emu('ant', action_repeat=2), s, 4, n)

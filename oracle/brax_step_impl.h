@@ -18,6 +18,30 @@
 #define CAT(a, b) CAT_(a, b)
 #define FN(name) CAT(name, SUFFIX)
 
+#ifndef BRAX_BRANCH_CTL
+#define BRAX_BRANCH_CTL
+/* Test aid (tests/_parity.py "two-branch check"): every DISCONTINUOUS predicate of the algorithm -- a contact's
+ * pen > 0, nv < 0, J > 0, |v_d| > 0.01 and the actuator cut-off at a joint limit -- goes through branch_pred with
+ * its distance from the switching point (velocity units; lengths and angles x100). The distance feeds the env's
+ * margin (brax_v1._note_margin); with a BranchCtl, evaluations closer than `thr` are counted (in evaluation order)
+ * and the k-th one is INVERTED when bit k of `mask` is set, so a test can ask "what if rounding had taken the
+ * other branch here?". cause[]: the smallest distance seen per predicate class (0-3 ground pen/nv/J/nd, 4-7 the
+ * same for walls, 8 actuator cut-off). mask = 0 changes nothing. */
+#define BRAX_NCAUSE 9
+typedef struct { double thr; unsigned mask; int count; double cause[BRAX_NCAUSE]; } BranchCtl;
+static inline int branch_pred(int truth, double dist, int cause, BranchCtl *bc, double *mg) {
+    if (mg && dist < *mg) *mg = dist;
+    if (bc) {
+        if (dist < bc->cause[cause]) bc->cause[cause] = dist;
+        if (dist < bc->thr) {
+            int k = bc->count++;
+            if (k < 32 && ((bc->mask >> k) & 1u)) truth = !truth;
+        }
+    }
+    return truth;
+}
+#endif
+
 typedef struct {
     int nb, nj, na, ncp, ncap, nbox, substeps, ground, arena;
     REAL h, vel_damp, ang_damp, baumgarte, friction, elasticity;
@@ -62,7 +86,7 @@ static inline void FN(quat_mul)(const REAL *u, const REAL *v, REAL *o) {
 
 /* brax_v1.System._impulse for one contact of body b; adds nothing, returns dvel/dang of this contact. */
 static inline void FN(impulse)(const FN(SysDesc) *S, int b, const REAL *bpos, const REAL *cpos, const REAL *cvel,
-                               const REAL *n, REAL pen, REAL *dvel, REAL *dang, double *mg) {
+                               const REAL *n, REAL pen, REAL *dvel, REAL *dang, double *mg, BranchCtl *bc, int wall) {
     const REAL one = 1, zero = 0;
     REAL mass = S->mass[b]; const REAL *ii = S->inv_inertia + 3 * b;
     REAL inv_m = one / mass;
@@ -86,20 +110,16 @@ static inline void FN(impulse)(const FN(SysDesc) *S, int b, const REAL *bpos, co
     for (int i = 0; i < 3; i++) Jdv[i] = -Jd * (vd[i] / dd);
     FN(cross3)(rel, Jdv, pd_a);
     for (int i = 0; i < 3; i++) { pd_v[i] = Jdv[i] / mass; pd_a[i] = ii[i] * pd_a[i]; }
-    REAL an = (pen > zero && nv < zero && J > zero) ? one : zero;
-    REAL ad = an * (nd > (REAL)0.01 ? one : zero);
+    /* apply_n = (pen > 0) & (nv < 0) & (J > 0); apply_d = apply_n & (nd > 0.01): each predicate through branch_pred
+     * (margin bookkeeping of brax_v1.System._note_margin: a later predicate only counts while the earlier ones hold) */
+    const int c0 = wall ? 4 : 0;
+    int live = branch_pred(pen > zero, fabs((double)pen) * 100.0, c0, bc, mg);
+    if (live) live = branch_pred(nv < zero, fabs((double)nv), c0 + 1, bc, mg);
+    if (live) live = branch_pred(J > zero, fabs((double)J), c0 + 2, bc, mg);
+    int drag = live ? branch_pred(nd > (REAL)0.01, fabs((double)nd - 0.01), c0 + 3, bc, mg) : 0;
+    REAL an = live ? one : zero;
+    REAL ad = an * (drag ? one : zero);
     for (int i = 0; i < 3; i++) { dvel[i] = pn_v[i] * an + pd_v[i] * ad; dang[i] = pn_a[i] * an + pd_a[i] * ad; }
-    if (mg) {   /* brax_v1.System._note_margin: distance to the nearest discontinuous branch (test aid) */
-        double m = fabs((double)pen) * 100.0;
-        if (pen > zero) {
-            m = fmin(m, fabs((double)nv));
-            if (nv < zero) {
-                m = fmin(m, fabs((double)J));
-                if (J > zero) m = fmin(m, fabs((double)nd - 0.01));
-            }
-        }
-        *mg = fmin(*mg, m);
-    }
 }
 
 /* g(t) of brax_v1.System._closest_segment_box */
@@ -136,7 +156,7 @@ static void FN(closest_segment_box)(const REAL *a, const REAL *b, const REAL *lo
 
 /* brax_v1.System._contacts on one env: cv/ca [nb][3] = ground group + wall group */
 static void FN(contacts)(const FN(SysDesc) *S, const REAL *pos, const REAL *rot, const REAL *vel, const REAL *ang,
-                         REAL *cv, REAL *ca, double *mg) {
+                         REAL *cv, REAL *ca, double *mg, BranchCtl *bc) {
     const int nb = S->nb;
     REAL cnt[MAXB], sv[MAXB][3], sa[MAXB][3];
     for (int b = 0; b < nb; b++) for (int i = 0; i < 3; i++) { cv[3 * b + i] = 0; ca[3 * b + i] = 0; }
@@ -155,7 +175,7 @@ static void FN(contacts)(const FN(SysDesc) *S, const REAL *pos, const REAL *rot,
             FN(cross3)(ang + 3 * b, r, w);
             for (int i = 0; i < 3; i++) { cvel[i] = vel[3 * b + i] + w[i]; gp[i] = pos[3 * g + i] - cpos[i]; }
             REAL pen = FN(dot3)(gp, n);
-            FN(impulse)(S, b, p, cpos, cvel, n, pen, dv, da, mg);
+            FN(impulse)(S, b, p, cpos, cvel, n, pen, dv, da, mg, bc, 0);
             cnt[b] += (dv[0] != 0 || dv[1] != 0 || dv[2] != 0) ? (REAL)1 : (REAL)0;
             for (int i = 0; i < 3; i++) { sv[b][i] += dv[i]; sa[b][i] += da[i]; }
         }
@@ -197,7 +217,10 @@ static void FN(contacts)(const FN(SysDesc) *S, const REAL *pos, const REAL *rot,
                 REAL pen = rad - dist;
                 FN(cross3)(ang + 3 * b, r, w);
                 for (int i = 0; i < 3; i++) cvel[i] = vel[3 * b + i] + w[i];
-                FN(impulse)(S, b, p, bp, cvel, n, pen, dv, da, mg);
+                /* a segment point inside the box: dvec = 0 exactly => n = 0, nv = 0 and no impulse in any evaluation
+                 * order: not rounding-ambiguous, kept out of the margin / branch bookkeeping */
+                const int degenerate = dist == (REAL)0;
+                FN(impulse)(S, b, p, bp, cvel, n, pen, dv, da, degenerate ? 0 : mg, degenerate ? 0 : bc, 1);
                 cnt[b] += (dv[0] != 0 || dv[1] != 0 || dv[2] != 0) ? (REAL)1 : (REAL)0;
                 for (int i = 0; i < 3; i++) { sv[b][i] += dv[i]; sa[b][i] += da[i]; }
                 any = 1;
@@ -212,7 +235,7 @@ static void FN(contacts)(const FN(SysDesc) *S, const REAL *pos, const REAL *rot,
 
 /* brax_v1.System.substep on one env, in place; cvel/cang = this substep's contact impulses */
 static void FN(substep)(const FN(SysDesc) *S, REAL *pos, REAL *rot, REAL *vel, REAL *ang, const REAL *act,
-                        REAL *cvel, REAL *cang, double *mg) {
+                        REAL *cvel, REAL *cang, double *mg, BranchCtl *bc) {
     const int nb = S->nb, nj = S->nj;
     const REAL h = S->h;
     /* kinetic */
@@ -230,6 +253,7 @@ static void FN(substep)(const FN(SysDesc) *S, REAL *pos, REAL *rot, REAL *vel, R
     /* joints + actuators (_joints_and_actuators) */
     REAL dvel[MAXB][3], dang[MAXB][3], adang[MAXB][3];
     REAL jdv_p[MAXJ][3], jda_p[MAXJ][3], jdv_c[MAXJ][3], jda_c[MAXJ][3], axis_p[MAXJ][3], psi[MAXJ];
+    int act_out[MAXJ];
     for (int b = 0; b < nb; b++) for (int i = 0; i < 3; i++) dvel[b][i] = dang[b][i] = adang[b][i] = 0;
     for (int j = 0; j < nj; j++) {
         const int P = S->j_parent[j], C = S->j_child[j];
@@ -261,8 +285,12 @@ static void FN(substep)(const FN(SysDesc) *S, REAL *pos, REAL *rot, REAL *vel, R
         REAL lo = S->j_limit[2 * j], hi = S->j_limit[2 * j + 1];
         REAL da = psi[j] < lo ? lo - psi[j] : (REAL)0;
         if (psi[j] > hi) da = hi - psi[j];
-        if (mg)   /* the actuator switches off discontinuously at the joint limits (brax_v1._joints_and_actuators) */
-            *mg = fmin(*mg, fmin(fabs((double)(REAL)(psi[j] - lo)), fabs((double)(REAL)(psi[j] - hi))) * 100.0);
+        /* the actuator switches off discontinuously outside the joint limits (brax_v1._joints_and_actuators); the
+         * limit torque itself (da) is continuous through 0 */
+        {
+            double dl = fabs((double)(REAL)(psi[j] - lo)), dh = fabs((double)(REAL)(psi[j] - hi));
+            act_out[j] = branch_pred(psi[j] < lo || psi[j] > hi, (dl < dh ? dl : dh) * 100.0, 8, bc, mg);
+        }
         for (int i = 0; i < 3; i++) {
             REAL t = S->j_stiff[j] * tq[i];
             t = t - S->j_lstr[j] * axis_p[j][i] * da;
@@ -279,7 +307,7 @@ static void FN(substep)(const FN(SysDesc) *S, REAL *pos, REAL *rot, REAL *vel, R
     for (int k = 0; k < S->na; k++) {
         int j = S->a_joint[k];
         REAL t = act[k] * S->a_strength[k];
-        if (psi[j] < S->j_limit[2 * j] || psi[j] > S->j_limit[2 * j + 1]) t = 0;
+        if (act_out[j]) t = 0;
         for (int i = 0; i < 3; i++) atau[k][i] = -(axis_p[j][i] * t);
     }
     for (int k = 0; k < S->na; k++) { int P = S->j_parent[S->a_joint[k]];
@@ -297,7 +325,7 @@ static void FN(substep)(const FN(SysDesc) *S, REAL *pos, REAL *rot, REAL *vel, R
         }
     }
     /* contacts -> collision */
-    FN(contacts)(S, pos, rot, vel, ang, cvel, cang, mg);
+    FN(contacts)(S, pos, rot, vel, ang, cvel, cang, mg, bc);
     for (int b = 0; b < nb; b++) {
         REAL m = S->active[b];
         for (int i = 0; i < 3; i++) {
@@ -309,11 +337,16 @@ static void FN(substep)(const FN(SysDesc) *S, REAL *pos, REAL *rot, REAL *vel, R
 
 /* System.step on N envs in place (QP arrays [N][nb][3|4], act [N][na]); cv/ca [N][nb][3] = summed contact impulses;
  * margin [N] (may be NULL) = the env's distance from its nearest discontinuous branch in this step (_note_margin).
+ * Two-branch test aid (all may be NULL): flip_mask [N] = which of the env's marginal predicate evaluations (those
+ * closer than flip_thr, in evaluation order) to invert; n_marginal [N] <- how many there were; cause [N][BRAX_NCAUSE]
+ * <- smallest distance per predicate class.
  * threads <= 0: OpenMP default. Returns 0, or -1 if the system exceeds the static limits. */
 int FN(brax_step)(const FN(SysDesc) *S, long N, REAL *pos, REAL *rot, REAL *vel, REAL *ang, const REAL *act,
-                  REAL *cv, REAL *ca, double *margin, int threads) {
+                  REAL *cv, REAL *ca, double *margin, int threads, const unsigned *flip_mask, double flip_thr,
+                  int *n_marginal, double *cause) {
     if (S->nb > MAXB || S->nj > MAXJ || S->na > MAXJ) return -1;
     const int nb = S->nb;
+    const int ctl = flip_mask || n_marginal || cause;
 #ifdef _OPENMP
     if (threads <= 0) threads = omp_get_max_threads();
 #pragma omp parallel for schedule(static) num_threads(threads)
@@ -325,10 +358,17 @@ int FN(brax_step)(const FN(SysDesc) *S, long N, REAL *pos, REAL *rot, REAL *vel,
         for (int i = 0; i < 3 * nb; i++) { ocv[i] = 0; oca[i] = 0; }
         double *mg = margin ? margin + e : 0;
         if (mg) *mg = 1e9;
+        BranchCtl bcs, *bc = ctl ? &bcs : 0;
+        if (bc) {
+            bc->thr = flip_thr; bc->mask = flip_mask ? flip_mask[e] : 0u; bc->count = 0;
+            for (int i = 0; i < BRAX_NCAUSE; i++) bc->cause[i] = 1e9;
+        }
         for (int s = 0; s < S->substeps; s++) {
-            FN(substep)(S, p, q, v, w, act + e * S->na, dv, da, mg);
+            FN(substep)(S, p, q, v, w, act + e * S->na, dv, da, mg, bc);
             for (int i = 0; i < 3 * nb; i++) { ocv[i] = ocv[i] + dv[i]; oca[i] = oca[i] + da[i]; }
         }
+        if (n_marginal) n_marginal[e] = bc->count;
+        if (cause) for (int i = 0; i < BRAX_NCAUSE; i++) cause[e * BRAX_NCAUSE + i] = bc->cause[i];
     }
     return 0;
 }
@@ -343,7 +383,7 @@ int FN(brax_info)(const FN(SysDesc) *S, long N, const REAL *pos, const REAL *rot
 #pragma omp parallel for schedule(static) num_threads(threads)
 #endif
     for (long e = 0; e < N; e++)
-        FN(contacts)(S, pos + e * nb * 3, rot + e * nb * 4, vel + e * nb * 3, ang + e * nb * 3, cv + e * nb * 3, ca + e * nb * 3, 0);
+        FN(contacts)(S, pos + e * nb * 3, rot + e * nb * 4, vel + e * nb * 3, ang + e * nb * 3, cv + e * nb * 3, ca + e * nb * 3, 0, 0);
     return 0;
 }
 

@@ -23,6 +23,9 @@ SRC = os.path.join(HERE, 'brax_step.c')
 HDR = os.path.join(HERE, 'brax_step_impl.h')
 OUT = os.path.join(HERE, '_build', 'libbraxstep.so')
 _lib = None
+N_CAUSE = 9   # BRAX_NCAUSE
+CAUSES = ('ground pen', 'ground nv', 'ground J', 'ground |v_d|', 'wall pen', 'wall nv', 'wall J', 'wall |v_d|',
+          'actuator cut-off')
 
 
 def build(force=False):
@@ -106,21 +109,34 @@ class CBackend:
     def _c(self, a):
         return np.ascontiguousarray(a, self.dtype)
 
-    def step(self, qp: bx.QP, act):
-        """System.step(qp, act) -> (qp', Info); the inputs are not modified."""
+    def step(self, qp: bx.QP, act, flip_mask=None, flip_thr=0.0, want_causes=False):
+        """System.step(qp, act) -> (qp', Info); the inputs are not modified.
+
+        Two-branch test aid (brax_step_impl.h BranchCtl): with `flip_thr` > 0 the step also counts, per env, the
+        evaluations of a discontinuous predicate that were closer than flip_thr to their switching point
+        (-> self.n_marginal [N]); `flip_mask` uint32 [N] inverts the k-th such evaluation where bit k is set;
+        want_causes -> self.cause_margin [N, 9] (ground pen/nv/J/nd, wall pen/nv/J/nd, actuator cut-off)."""
         pos, rot, vel, ang = (self._c(x).copy() for x in (qp.pos, qp.rot, qp.vel, qp.ang))
         act = self._c(act)
         n = pos.shape[0]
         assert pos.shape == (n, self.nb, 3) and rot.shape == (n, self.nb, 4) and act.shape == (n, self.na)
         cv, ca = np.empty_like(pos), np.empty_like(pos)
         mg = np.empty(n, np.float64) if self.system.track_margin else None
-        rc = self._step(C.byref(self.desc), C.c_long(n), *[C.c_void_p(x.ctypes.data) for x in
-                                                           (pos, rot, vel, ang, act, cv, ca)],
-                        C.c_void_p(mg.ctypes.data if mg is not None else None), C.c_int(self.threads))
+        ctl = flip_thr > 0 or flip_mask is not None
+        fm = None if flip_mask is None else np.ascontiguousarray(flip_mask, np.uint32)
+        assert fm is None or fm.shape == (n,)
+        nm = np.zeros(n, np.int32) if ctl else None
+        cause = np.empty((n, N_CAUSE), np.float64) if want_causes else None
+
+        def ptr(a):
+            return C.c_void_p(a.ctypes.data if a is not None and a.size else None)
+        rc = self._step(C.byref(self.desc), C.c_long(n), *[ptr(x) for x in (pos, rot, vel, ang, act, cv, ca)],
+                        ptr(mg), C.c_int(self.threads), ptr(fm), C.c_double(flip_thr), ptr(nm), ptr(cause))
         if rc:
             raise RuntimeError(f'brax_step{self.sfx} failed: {rc}')
         if mg is not None:   # same protocol as the NumPy text: the caller clears system.margin before a step
             self.system.margin = mg if self.system.margin is None else np.minimum(self.system.margin, mg)
+        self.n_marginal, self.cause_margin = nm, cause
         return bx.QP(pos, rot, vel, ang), bx.Info(cv, ca)
 
     def info(self, qp: bx.QP):

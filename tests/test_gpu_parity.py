@@ -112,16 +112,16 @@ def test_step_teacher_forced(kind):
 
 
 def test_step_teacher_forced_long_heavenhell():
-    """BASELINE config 1 (Ant-HeavenHell, 128 envs, random-action rollout), teacher-forced deeper into the episode
-    (ants against walls, fallen ants, finished envs); POBRAX_LONG_T=1000 runs the full length (~2 min of oracle)."""
-    _teacher_forced('ant_heavenhell', 128, int(os.environ.get('POBRAX_LONG_T', '120')))
+    """BASELINE config 1 (Ant-HeavenHell, 128 envs, 1000-step random-action rollout), teacher-forced over the whole
+    episode length (ants against walls, fallen ants, finished envs). POBRAX_LONG_T shortens it for quick runs."""
+    _teacher_forced('ant_heavenhell', 128, int(os.environ.get('POBRAX_LONG_T', '1000')), c_step=True)
 
 
 def test_step_teacher_forced_corner_walls():
     """HeavenHell ants spawned around the staircase corner of the T junction (wall boxes x in [2, 3] up to y = 5.5 and
     y in [5, 6] from x = 2.5): two candidate walls per cell, Aux / torso wall contacts, closest points inside the
     segment (bisection) -- the out-of-line wall groups and the multi-candidate cull against the oracle."""
-    st = _teacher_forced('ant_heavenhell', 128, 40, init_box=((1.3, 4.9), (2.0, 5.9)), min_clear=0.5)
+    st = _teacher_forced('ant_heavenhell', 128, 40, init_box=((1.3, 4.9), (2.0, 5.9)))
     assert st['aux_wall_contacts'] > 20 and st['torso_contacts'] > 0, st   # the scenario does reach those colliders
 
 
@@ -130,16 +130,23 @@ def test_step_teacher_forced_corner_walls():
 def test_step_teacher_forced_at_baseline_sizes(kind, n, T):
     """BASELINE configs 2-4 at their full batch sizes and config 5 at its 8-GPU shard size (1 Mi / 8), teacher-forced
     against the scalar C twin of the oracle (oracle/brax_step.c on all host cores; tests/test_oracle_c.py pins it to
-    the NumPy text and to the golden rollout) under the NumPy task logic: every env of the batch is compared."""
-    _teacher_forced(kind, n, T, c_step=True)   # >= 75 % of the envs are held to the tight gates (HeavenHell: 77 %)
+    the NumPy text and to the golden rollout) under the NumPy task logic: every env of the batch is compared, and at
+    most 1 % of them may be 'unexplained' (tests/_parity.py TwoBranch)."""
+    st = _teacher_forced(kind, n, T, c_step=True)
+    print(f'\n[parity] {kind} n={n} T={T}: {st}')
 
 
-def _teacher_forced(kind, n, T, init_box=None, min_clear=0.75, c_step=False):
+def _teacher_forced(kind, n, T, init_box=None, c_step=False):
+    """One env step from identical states, T times along an oracle rollout. Every env must meet the TIGHT gates of
+    tests/_parity.py against the oracle's step -- or, where the oracle reports a rounding-ambiguous contact / actuator
+    decision in that step, against the oracle's step with some of those decisions taken the other way (two-branch
+    check). Envs that match neither are 'unexplained': loose bound, and at most 1 % of the batch in any step."""
     keys = P.keys_for(n, seed=0)
     oenv = oenvs.ENVS[kind]()
     if c_step:
         from oracle import cstep
         cstep.attach(oenv.sys, threads=os.cpu_count() or 1)
+    two = P.TwoBranch(lambda: oenvs.ENVS[kind]().sys)
     nb = oenv.sys.num_bodies
     kw = {}
     if init_box is not None:   # ant_heavenhell.py:73 self._init_ant_pos
@@ -149,8 +156,8 @@ def _teacher_forced(kind, n, T, init_box=None, min_clear=0.75, c_step=False):
     env = _make(kind, n, auto_reset=False, episode_length=1000, **kw)
     rng = tf.prng_key(1)
     oenv.sys.track_margin = True
-    compared = []
-    stats = {'aux_wall_contacts': 0, 'torso_contacts': 0}
+    stats = {'aux_wall_contacts': 0, 'torso_contacts': 0, 'marginal': 0.0, 'other_branch': 0, 'unexplained': 0,
+             'worst_unexplained_share': 0.0}
     Pc = 1 if kind == 'ant' else 3
     for t in range(T):
         rng, a = P.actions_for(rng, n)
@@ -160,42 +167,63 @@ def _teacher_forced(kind, n, T, init_box=None, min_clear=0.75, c_step=False):
         got = env.step(cs, torch.as_tensor(a, device='cuda'))
         torch.cuda.synchronize()
         # Envs in which some contact sat within rounding noise of a discontinuous branch of the reference
-        # algorithm (touching / approaching / J > 0 / |v_d| > 0.01; oracle/brax_v1.py:_note_margin) may take the
-        # other branch under any other float32 evaluation order: they get a loose bound, the rest the tight one.
+        # algorithm (touching / approaching / J > 0 / |v_d| > 0.01 / actuator cut-off; oracle/brax_v1.py:_note_margin)
+        # may take the other branch under any other float32 evaluation order (XLA's included).
         clear = oenv.sys.margin > P.BRANCH_MARGIN
-        compared.append(clear.mean())
+        g = P.Got.from_state(got, kind, nb)
+        base_ok = P.physics_match(g, nxt.qp, bx_info_from_obs(nxt.obs, Pc, nb))
+        assert base_ok[clear].all(), (f'{kind} t={t}: {int((clear & ~base_ok).sum())} unambiguous envs off the tight '
+                                      f'gates, first {np.nonzero(clear & ~base_ok)[0][:6].tolist()}')
+        rest = np.nonzero(~clear & ~base_ok)[0]
+        explained, _ = two.explain(s.qp, a, rest, g)
+        bad = rest[~explained]
+        stats['marginal'] += float((~clear).mean()) / T
+        stats['other_branch'] += int(explained.sum())
+        stats['unexplained'] += len(bad)
+        stats['worst_unexplained_share'] = max(stats['worst_unexplained_share'], len(bad) / n)
+        assert len(bad) <= max(1, P.MAX_UNEXPLAINED * n), f'{kind} t={t}: {len(bad)} of {n} envs match neither branch'
         cvel = nxt.obs[:, Pc + 26:Pc + 26 + 3 * nb].reshape(n, nb, 3)   # clip(contact.vel): Aux bodies only touch walls
         stats['aux_wall_contacts'] += int((np.abs(cvel[:, [1, 3, 5, 7]]).sum(-1) > 0).sum())
         stats['torso_contacts'] += int((np.abs(cvel[:, 0]).sum(-1) > 0).sum())
-        P.assert_qp_close(got.qp, nxt.qp, f'{kind} t={t}', rows=clear)
-        P.assert_qp_close(got.qp, nxt.qp, f'{kind} t={t} (ambiguous envs)', rows=~clear, loose=True)
+        same = np.ones(n, bool)      # envs on the oracle's own branch: everything below is compared against `nxt`
+        same[rest] = False
+        P.assert_qp_close(got.qp, nxt.qp, f'{kind} t={t}', rows=same)
+        P.assert_qp_close(got.qp, nxt.qp, f'{kind} t={t} (unexplained envs)', rows=bad, loose=True)
         assert np.array_equal(P.t2n(got.done), np.asarray(nxt.done, np.float32)), f'{kind} t={t} done'
         if kind == 'ant':
             # forward = dx / dt amplifies the pos tolerance x20
-            assert (np.abs(P.t2n(got.reward) - nxt.reward)[clear] <= 2e-4).all(), f'{kind} t={t} reward'
+            assert (np.abs(P.t2n(got.reward) - nxt.reward)[same] <= 2e-4).all(), f'{kind} t={t} reward'
         else:
             assert np.array_equal(P.t2n(got.reward), nxt.reward), f'{kind} t={t} reward'
         if kind == 'ant_tag':
             assert (P.rng_bits(got.info['rng']) == nxt.info['rng']).all()
             assert np.array_equal(P.t2n(got.metrics['hits']), nxt.metrics['hits'])
             # the opponent moves along (ant - target)/|ant - target| of the post-physics ant: float tolerance
-            # (tight where the ant's own step is unambiguous; an env that took the other contact branch moves its
-            # opponent along a slightly different direction)
+            # (tight where the ant's own step took the oracle's branch; an env on the other contact branch moves
+            # its opponent along a slightly different direction)
             dtgt = np.abs(P.t2n(got.qp.pos)[:, oenv.target_idx] - nxt.qp.pos[:, oenv.target_idx]).max(axis=-1)
-            assert dtgt[clear].max() <= 1e-5 and dtgt.max() <= P.LOOSE_POS, (dtgt[clear].max(), dtgt.max())
+            assert dtgt[same].max() <= 1e-5 and dtgt.max() <= P.LOOSE_POS, (dtgt[same].max(), dtgt.max())
         if kind == 'ant_gather':
             assert np.array_equal(P.t2n(got.metrics['apples']), nxt.metrics['apples'].astype(np.float32))
             assert np.array_equal(P.t2n(got.metrics['bombs']), nxt.metrics['bombs'].astype(np.float32))
             assert np.array_equal(P.t2n(got.qp.pos)[:, oenv.obj], nxt.qp.pos[:, oenv.obj])
         mask = np.ones_like(nxt.obs, bool)
-        mask[~clear] = False
+        mask[~same] = False       # other-branch envs: qp and contact columns were checked against their own branch
         if kind == 'ant_gather':  # a sensor bin index is int(trunc(angle / res)): tolerate angles on a bin edge
             mask[:, -2 * oenv.n_bins:] &= _gather_reading_mask(oenv, nxt, got)
         P.assert_obs_close(P.t2n(got.obs), nxt.obs, kind, nb, f'{kind} t={t}', mask=mask)
         s = nxt
-    assert np.mean(compared) > min_clear, compared
-    stats['clear'] = float(np.mean(compared))
     return stats
+
+
+class bx_info_from_obs:
+    """Info-like view of the oracle observation's (already clipped) contact columns, for P.physics_match."""
+
+    def __init__(self, obs, Pc, nb):
+        n = obs.shape[0]
+        c0 = Pc + 26
+        self.contact_vel = obs[:, c0:c0 + 3 * nb].reshape(n, nb, 3)
+        self.contact_ang = obs[:, c0 + 3 * nb:c0 + 6 * nb].reshape(n, nb, 3)
 
 
 def _gather_reading_mask(oenv, nxt, got):
@@ -213,24 +241,40 @@ def _gather_reading_mask(oenv, nxt, got):
 
 @pytest.mark.parametrize('kind', ['ant_heavenhell', 'ant_tag'])
 def test_free_running_20_steps(kind):
-    """Free-running rollout; SURVEY App. C gate: <= 3e-5 abs on pos/rot after 20 steps (chaos sets in later)."""
-    n, T = 64, 20
+    """Free-running rollout, 20 steps (chaos sets in later). Gate over EVERY env whose 20 steps stayed clear of a
+    rounding-ambiguous decision (the oracle's own margins): max |d pos|, |d rot| <= 1e-4, and the SURVEY App. C figure
+    (3e-5, measured there on one env) for >= 95 % of them. Basis: the device text under g++ (tests/host_emu) is
+    2.1e-5 / 3.6e-5 (HeavenHell / Tag) at worst over ~220 clear envs after 20 steps, 90th percentile 0.8e-5 / 1.3e-5
+    -- errors grow ~3x per 5 steps, so a hard max over hundreds of envs sits above a single env's figure. An env
+    that did pass through an ambiguous decision may legitimately be one contact impulse apart: not gated here (the
+    teacher-forced two-branch tests cover those steps)."""
+    n, T = 256, 20
     keys = P.keys_for(n, seed=3)
     oenv = oenvs.ENVS[kind]()
+    from oracle import cstep
+    cstep.attach(oenv.sys, threads=os.cpu_count() or 1)
+    oenv.sys.track_margin = True
     s = oenv.reset(keys)
     env = _make(kind, n, auto_reset=False)
     cs = env.reset(keys)
     rng = tf.prng_key(1)
+    dirty = np.zeros(n, bool)
     for t in range(T):
         rng, a = P.actions_for(rng, n)
+        oenv.sys.margin = None
         s = oenv.step(s, a)
+        dirty |= oenv.sys.margin <= P.BRANCH_MARGIN
         cs = env.step(cs, torch.as_tensor(a, device='cuda'))
     q = cs.qp
-    # envs whose reset had a rounding-ambiguous contact start from (legitimately) different impulses
     err = np.maximum(np.abs(P.t2n(q.pos)[:, :9] - s.qp.pos[:, :9]).reshape(n, -1).max(1),
                      np.abs(P.t2n(q.rot)[:, :9] - s.qp.rot[:, :9]).reshape(n, -1).max(1))
-    assert np.quantile(err, 0.9) <= 3e-5, np.sort(err)[-8:]
-    assert np.median(err) <= 1e-5
+    clear = ~dirty
+    assert clear.mean() > 0.25, clear.mean()
+    print(f'\n[parity] free-running {kind}: {int(clear.sum())} clear envs, max {err[clear].max():.2e}, '
+          f'q95 {np.quantile(err[clear], 0.95):.2e}, median {np.median(err[clear]):.2e}')
+    assert err[clear].max() <= 1e-4, np.sort(err[clear])[-8:]
+    assert np.quantile(err[clear], 0.95) <= 3e-5, np.sort(err[clear])[-8:]
+    assert np.median(err[clear]) <= 1e-5
 
 
 @pytest.mark.parametrize('kind,n,T', [('ant_heavenhell', 4096, 400), ('ant_tag', 4096, 300), ('ant_gather', 2048, 300),

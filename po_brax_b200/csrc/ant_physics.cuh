@@ -55,10 +55,7 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
 
 // Bare MUFU.RSQ / MUFU.RCP (no denormal-range fix-up code): the arguments here are never denormal -- quaternion
 // norms, 1/m + lever^2, 1e-6 + |v|, max(|sin|, |cos|). sqrt_pos: sqrt to ~2 ulp for lengths (0 below 1e-15).
-#ifdef POBRAX_HOST_EMU   // tests/host_emu: correctly rounded stand-ins for the two MUFU forms
-inline float rsqrt_ftz(float x) { return 1.0f / sqrtf(x); }
-inline float rcp_ftz(float x) { return 1.0f / x; }
-#else
+#ifndef POBRAX_HOST_EMU   // (tests/host_emu supplies correctly rounded stand-ins from its shim header)
 __device__ __forceinline__ float rsqrt_ftz(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rcp_ftz(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #endif
@@ -176,16 +173,12 @@ __device__ __forceinline__ Imp contact_general(V3 p, V3 e, V3 v, V3 w, float rad
 // cell = floor((p - origin) / cell_size) is one FMA per axis here, and the texture unit does the float -> cell
 // conversion, the clamp onto the border cells (which list every wall, as does everything outside the table) and the
 // addressing -- 3 instructions per lookup instead of 10 (30 lookups per lane and step).
+#ifndef POBRAX_HOST_EMU   // (tests/host_emu reads the host copy of the tables from its shim header)
 __device__ __forceinline__ unsigned wall_mask_at(const DevConst& C, int kind, float x, float y) {
-#ifdef POBRAX_HOST_EMU   // tests/host_emu: C.wall_tex points at the host copy of the tables; floor + clamp by hand
-  const int ix = (int)fminf(fmaxf(floorf(fmaf(x, C.sdf_inv_cell, C.sdf_bx)), 0.0f), (float)(C.sdf_nx - 1));
-  const int iy = (int)fminf(fmaxf(floorf(fmaf(y, C.sdf_inv_cell, C.sdf_by)), 0.0f), (float)(C.sdf_ny - 1));
-  return reinterpret_cast<const unsigned char*>(C.wall_tex)[((size_t)kind * C.sdf_ny + iy) * C.sdf_nx + ix];
-#else
   return tex2DLayered<unsigned char>((cudaTextureObject_t)C.wall_tex, fmaf(x, C.sdf_inv_cell, C.sdf_bx),
                                      fmaf(y, C.sdf_inv_cell, C.sdf_by), kind);
-#endif
 }
+#endif
 
 // Per-lane constants of leg l.
 struct LegK {

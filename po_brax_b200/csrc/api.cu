@@ -23,6 +23,7 @@ cudaError_t launch_pack(const DevConst& C, const float* pos, const float* rot, c
 cudaError_t launch_split_keys(const uint32_t key[2], int n, int first, int count, uint32_t* out, cudaStream_t st);
 cudaError_t launch_fma_probe(float* out, int blocks, int iters, cudaStream_t st);
 cudaError_t launch_split_pairs(const uint32_t* keys, int n, uint32_t* a, uint32_t* b, cudaStream_t st);
+cudaError_t setup_device(DevConst& C, size_t smem_limit, const char** what);
 
 struct Handle {
   DevConst C;
@@ -206,12 +207,14 @@ extern "C" int pobrax_layout(const PobraxParams* p, PobraxLayout* out) {
 }
 
 static std::vector<float2> gather_grid(const PobraxParams* p) {
-  // ant_gather.py:88-90: integer (x, y), meshgrid 'xy' order (y-major, x fastest), |g| > spacing
+  // ant_gather.py:88-90: meshgrid(arange(-cage_x, cage_x + 1), arange(-cage_y, cage_y + 1)) in 'xy' order (y-major, x
+  // fastest), |g| > spacing. arange keeps a fractional origin (cage 4.5 -> -4.5, -3.5, ..., 4.5), like the reference.
   std::vector<float2> g;
-  const int cx = (int)p->gather_cage_xy[0], cy = (int)p->gather_cage_xy[1];
-  for (int y = -cy; y <= cy; ++y)
-    for (int x = -cx; x <= cx; ++x) {
-      const float fx = (float)x, fy = (float)y;
+  const double cx = p->gather_cage_xy[0], cy = p->gather_cage_xy[1];
+  const int nx = (int)std::ceil((cx + 1.0) - (-cx) - 1e-9), ny = (int)std::ceil((cy + 1.0) - (-cy) - 1e-9);
+  for (int iy = 0; iy < ny; ++iy)
+    for (int ix = 0; ix < nx; ++ix) {
+      const float fx = (float)(-cx + ix), fy = (float)(-cy + iy);
       if (std::sqrt(fx * fx + fy * fy) > p->robot_object_spacing) g.push_back(make_float2(fx, fy));
     }
   return g;
@@ -370,6 +373,9 @@ static int build_dev_const(const PobraxParams* p, DevConst* Cp, std::vector<uint
   C.spacing = p->robot_object_spacing;
   grid->clear();
   if (p->env_kind == POBRAX_ANT_GATHER) {
+    if (!(p->gather_cage_xy[0] >= 0.0f) || !(p->gather_cage_xy[1] >= 0.0f) || p->gather_cage_xy[0] > 64.0f ||
+        p->gather_cage_xy[1] > 64.0f)
+      return fail("gather: cage_xy must be in [0, 64]");
     *grid = gather_grid(p);
     if ((int)grid->size() < p->n_apples + p->n_bombs) return fail("gather: fewer grid cells than objects");
     if (grid->size() > 1024) return fail("gather: cage too large (more than 1024 candidate cells)");
@@ -377,7 +383,6 @@ static int build_dev_const(const PobraxParams* p, DevConst* Cp, std::vector<uint
     // ant_gather.py:91: waiting_area = last grid position + 2*sensor_range
     C.waiting[0] = grid->back().x + p->sensor_range * 2; C.waiting[1] = grid->back().y + p->sensor_range * 2;
     C.waiting[2] = 0.0f + p->sensor_range * 2;
-    C.gather_cx = (int)p->gather_cage_xy[0]; C.gather_cy = (int)p->gather_cage_xy[1];
   }
   return 0;
 }
@@ -437,6 +442,13 @@ extern "C" int pobrax_create(const PobraxParams* p, int device, void** handle) {
     C.wall_tex = (unsigned long long)h->sdf_tex;
   }
   C.walls = h->walls;
+  {  // per-device kernel attributes + occupancy for THIS handle's device (a process may hold handles on several GPUs)
+    const char* what = "";
+    if ((e = pobrax::setup_device(C, (size_t)prop.sharedMemPerBlockOptin, &what)) != cudaSuccess) {
+      cudaSetDevice(prev); pobrax_destroy(h);
+      return fail_cuda((std::string("pobrax_create: ") + what).c_str(), e);
+    }
+  }
   h->C = C;
   cudaSetDevice(prev);
   *handle = h;

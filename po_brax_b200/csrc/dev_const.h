@@ -65,7 +65,6 @@ struct DevConst {
   float tag_radius, target_step, min_spawn, cage_xy[2];
   int32_t n_apples, n_bombs, n_bins, n_grid;
   float catch_range, sensor_range, half_span, bin_res, spacing, waiting[3];
-  int32_t gather_cx, gather_cy;              // integer cage half extents (grid -cx..cx x -cy..cy)
   float arena_z;                             // Arena body z (half height)
 };
 

@@ -821,27 +821,53 @@ __global__ void split_pairs_kernel(const uint32_t* __restrict__ keys, int n, uin
 static size_t obs_stage_bytes(const DevConst& C) { return (size_t)(kThreads / 32) * 8 * C.obs_dim * sizeof(float); }
 
 template <int KIND>
+static size_t step_smem_bytes(const DevConst& C) { return (size_t)(StepCfg<KIND>::threads / 32) * 8 * C.obs_dim * sizeof(float); }
+template <int KIND>
+static size_t reset_smem_bytes(const DevConst& C) {
+  size_t smem = obs_stage_bytes(C);
+  if (KIND == POBRAX_ANT_GATHER) smem += (size_t)kEnvsPerBlock * C.n_grid * sizeof(uint32_t);
+  return smem;
+}
+
+// Per-handle, per-device kernel setup (called by pobrax_create with the handle's device current): the dynamic
+// shared memory limits of this env family's step / reset kernels on THIS device (cudaFuncSetAttribute is per
+// device) and the step kernel's L2 prefetch distance (one full wave of resident CTAs; POBRAX_PREFETCH_CTAS
+// overrides, for tuning).
+template <int KIND>
+static cudaError_t setup_device_t(DevConst& C, size_t smem_limit, const char** what) {
+  const size_t ss = step_smem_bytes<KIND>(C), rs = reset_smem_bytes<KIND>(C);
+  if (ss > smem_limit) { *what = "step kernel: observation staging exceeds the device's shared memory per block"; return cudaErrorInvalidValue; }
+  if (rs > smem_limit) { *what = "reset kernel: observation staging + object grid exceed the device's shared memory per block (smaller cage_xy?)"; return cudaErrorInvalidValue; }
+  cudaError_t e;
+  *what = "cudaFuncSetAttribute(step_kernel, MaxDynamicSharedMemorySize)";
+  if ((e = cudaFuncSetAttribute(step_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess) return e;
+  *what = "cudaFuncSetAttribute(reset_kernel, MaxDynamicSharedMemorySize)";
+  if ((e = cudaFuncSetAttribute(reset_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs)) != cudaSuccess) return e;
+  int dev = 0, sms = 148, per_sm = StepCfg<KIND>::min_blocks;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  *what = "cudaOccupancyMaxActiveBlocksPerMultiprocessor(step_kernel)";
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<KIND>, StepCfg<KIND>::threads, ss)) != cudaSuccess) return e;
+  const char* ov = getenv("POBRAX_PREFETCH_CTAS");
+  C.prefetch_ctas = ov ? atoi(ov) : sms * per_sm;
+  return cudaSuccess;
+}
+
+cudaError_t setup_device(DevConst& C, size_t smem_limit, const char** what) {
+  switch (C.env_kind) {
+    case POBRAX_ANT: return setup_device_t<POBRAX_ANT>(C, smem_limit, what);
+    case POBRAX_ANT_HEAVENHELL: return setup_device_t<POBRAX_ANT_HEAVENHELL>(C, smem_limit, what);
+    case POBRAX_ANT_GATHER: return setup_device_t<POBRAX_ANT_GATHER>(C, smem_limit, what);
+    case POBRAX_ANT_TAG: return setup_device_t<POBRAX_ANT_TAG>(C, smem_limit, what);
+  }
+  *what = "unknown env_kind";
+  return cudaErrorInvalidValue;
+}
+
+template <int KIND>
 static cudaError_t launch_step_t(const DevConst& C, const PobraxState& S, const float* action, cudaStream_t st) {
-  const size_t smem = (size_t)(StepCfg<KIND>::threads / 32) * 8 * C.obs_dim * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(step_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr_set = true;
-  }
-  // L2 prefetch distance: one full wave of resident CTAs ahead (POBRAX_PREFETCH_CTAS overrides, for tuning)
-  static int prefetch_ctas = -1;
-  if (prefetch_ctas < 0) {
-    int dev = 0, sms = 148, per_sm = StepCfg<KIND>::min_blocks;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<KIND>, StepCfg<KIND>::threads, smem);
-    const char* ov = getenv("POBRAX_PREFETCH_CTAS");
-    prefetch_ctas = ov ? atoi(ov) : sms * per_sm;
-  }
-  DevConst Cl = C;
-  Cl.prefetch_ctas = prefetch_ctas;
   const int blocks = (C.n_envs + StepCfg<KIND>::envs - 1) / StepCfg<KIND>::envs;
-  step_kernel<KIND><<<blocks, StepCfg<KIND>::threads, smem, st>>>(Cl, S, action);
+  step_kernel<KIND><<<blocks, StepCfg<KIND>::threads, step_smem_bytes<KIND>(C), st>>>(C, S, action);
   return cudaGetLastError();
 }
 
@@ -857,15 +883,8 @@ __global__ void chain_advance_kernel(uint32_t* chain, int n_envs) {
 template <int KIND>
 static cudaError_t launch_reset_t(const DevConst& C, const PobraxState& S, const uint32_t* keys, const float2* grid,
                                   int only_done, uint32_t* chain, cudaStream_t st) {
-  size_t smem = obs_stage_bytes(C);
-  if (KIND == POBRAX_ANT_GATHER) smem += (size_t)kEnvsPerBlock * C.n_grid * sizeof(uint32_t);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(reset_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr_set = true;
-  }
   const int blocks = (C.n_envs + kEnvsPerBlock - 1) / kEnvsPerBlock;
-  reset_kernel<KIND><<<blocks, kThreads, smem, st>>>(C, S, keys, grid, only_done, chain);
+  reset_kernel<KIND><<<blocks, kThreads, reset_smem_bytes<KIND>(C), st>>>(C, S, keys, grid, only_done, chain);
   if (chain) chain_advance_kernel<<<1, 1, 0, st>>>(chain, C.n_envs);
   return cudaGetLastError();
 }

@@ -27,19 +27,8 @@ struct Body { V3 p; float qw, qx, qy, qz; V3 v, w; };
 // (pk(s, s) -> the .F32 operand form) and half swaps into the instruction's operand modifiers, and packing two
 // freshly computed scalars is free (they are allocated as a pair). Every operation rounds exactly like its scalar
 // counterpart (fma.rn / add.rn / mul.rn per half).
+#ifndef POBRAX_HOST_EMU   // (the g++ build of tests/host_emu supplies F2 and these primitives from its own shim header)
 struct F2 { unsigned long long v; };
-
-#ifdef POBRAX_HOST_EMU   // tests/host_emu (g++, no GPU): the same operation per half in plain C++, same rounding
-inline F2 pk(float lo, float hi) { unsigned a, b; memcpy(&a, &lo, 4); memcpy(&b, &hi, 4); F2 r; r.v = (unsigned long long)a | ((unsigned long long)b << 32); return r; }
-inline F2 bc(float s) { return pk(s, s); }
-inline float lo(F2 a) { unsigned u = (unsigned)a.v; float f; memcpy(&f, &u, 4); return f; }
-inline float hi(F2 a) { unsigned u = (unsigned)(a.v >> 32); float f; memcpy(&f, &u, 4); return f; }
-inline F2 neg(F2 a) { return pk(-lo(a), -hi(a)); }
-inline F2 operator+(F2 a, F2 b) { return pk(lo(a) + lo(b), hi(a) + hi(b)); }
-inline F2 operator-(F2 a, F2 b) { return pk(lo(a) - lo(b), hi(a) - hi(b)); }
-inline F2 operator*(F2 a, F2 b) { return pk(lo(a) * lo(b), hi(a) * hi(b)); }
-inline F2 fma2(F2 a, F2 b, F2 c) { return pk(fmaf(lo(a), lo(b), lo(c)), fmaf(hi(a), hi(b), hi(c))); }
-#else
 __device__ __forceinline__ F2 pk(float lo, float hi) { F2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ F2 bc(float s) { return pk(s, s); }
 __device__ __forceinline__ float lo(F2 a) { return __uint_as_float((unsigned)a.v); }
@@ -48,12 +37,10 @@ __device__ __forceinline__ F2 neg(F2 a) { return pk(-lo(a), -hi(a)); }
 __device__ __forceinline__ F2 operator+(F2 a, F2 b) { F2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 __device__ __forceinline__ F2 operator-(F2 a, F2 b) { F2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 __device__ __forceinline__ F2 operator*(F2 a, F2 b) { F2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) { F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
 #endif
 __device__ __forceinline__ F2 operator*(float s, F2 a) { return bc(s) * a; }
 // a*b + c, a*b - c, c - a*b
-#ifndef POBRAX_HOST_EMU
-__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) { F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
-#endif
 __device__ __forceinline__ F2 fma2(float a, F2 b, F2 c) { return fma2(bc(a), b, c); }
 __device__ __forceinline__ F2 fms2(F2 a, F2 b, F2 c) { return fma2(a, b, neg(c)); }
 __device__ __forceinline__ F2 fnma2(F2 a, F2 b, F2 c) { return fma2(neg(a), b, c); }

@@ -32,13 +32,15 @@ def create_gym_env(env_name: str, batch_size: Optional[int] = None, seed: int = 
     eval_metrics = kwargs.pop('eval_metrics', False)
     discount = kwargs.pop('discount', 1.)
     cuda_graph = kwargs.pop('cuda_graph', False)   # extension: replay the gym step as one CUDA graph (wrappers.py)
+    copy = kwargs.pop('copy', True)                # False: hand out the live device buffers (wrappers.py docstring)
     if batch_size is not None and batch_size <= 0:
         raise ValueError('`batch_size` should either be None or a positive integer.')
     environment = create(env_name=env_name, batch_size=batch_size, **kwargs)
     if batch_size is None:
         e = AutoresetGymWrapper(environment, seed=seed, backend=backend)
     else:
-        e = AutoresetVmapGymWrapper(environment, batch_size, seed=seed, backend=backend, cuda_graph=cuda_graph)
+        e = AutoresetVmapGymWrapper(environment, batch_size, seed=seed, backend=backend, cuda_graph=cuda_graph,
+                                    copy=copy)
     if eval_metrics:
         e = EvalGymWrapper(e, discount=discount)
     return e

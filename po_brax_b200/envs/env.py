@@ -9,7 +9,9 @@ All buffers are torch CUDA tensors owned by the State; the library only launches
 torch's current stream. The env is always batched (the reference's VmapWrapper axis); the wrapper
 stack ActionRepeat -> Episode -> Vmap -> AutoReset of `create()` is fused into the step kernel.
 """
+import collections
 import ctypes as C
+import math
 from typing import Dict, Optional
 
 import numpy as np
@@ -19,6 +21,84 @@ from .. import _lib
 
 KINDS = {'ant': _lib.ANT, 'ant_heavenhell': _lib.ANT_HEAVENHELL, 'ant_gather': _lib.ANT_GATHER,
          'ant_tag': _lib.ANT_TAG}
+
+
+_ANT_BODIES = ('$ Torso', 'Aux 1', '$ Body 4', 'Aux 2', '$ Body 7', 'Aux 3', '$ Body 10', 'Aux 4', '$ Body 13', 'Ground')
+
+
+def _body_names(env_name, n_apples=8, n_bombs=8):
+    """Body order of the reference systems (brax.envs.ant._SYSTEM_CONFIG + ant_heavenhell.py:17-32, ant_tag.py:16-24,
+    ant_gather.py:25-38): qp rows and sys.body.index."""
+    if env_name == 'ant':
+        return _ANT_BODIES
+    if env_name == 'ant_heavenhell':
+        return _ANT_BODIES + ('Priest', 'Target', 'Hell', 'Arena')
+    if env_name == 'ant_tag':
+        return _ANT_BODIES + ('Target', 'Arena')
+    return _ANT_BODIES + ('Arena',) + tuple(f'Target_{i + 1}' for i in range(n_apples)) + \
+        tuple(f'Bomb_{i + 1}' for i in range(n_bombs))
+
+
+class _Namespace:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class SysShim:
+    """The part of `env.sys` (brax.System) that code outside the env reads: `sys.config.dt` / `.substeps`
+    (/root/reference/po_brax/envs/wrappers.py:22-23,140), `sys.body.index[name]`, `sys.num_bodies`,
+    `sys.num_joint_dof` (ant_heavenhell.py:64-69,90), `sys.default_angle()`. The physics itself (sys.step / info /
+    default_qp) only exists fused inside the kernels: those attributes raise."""
+
+    def __init__(self, env):
+        p = env.params
+        names = _body_names(env.env_name, p.n_apples, p.n_bombs)
+        # ActionRepeatWrapper (wrappers.py:21-23) scales the config in place: dt *= k, substeps *= k
+        self.config = _Namespace(dt=float(p.dt) * p.action_repeat, substeps=int(p.substeps) * p.action_repeat,
+                                 bodies=[_Namespace(name=n) for n in names], gravity=(0.0, 0.0, float(p.gravity_z)),
+                                 friction=float(p.friction), elasticity=float(p.elasticity),
+                                 baumgarte_erp=float(p.baumgarte_erp), angular_damping=float(p.angular_damping),
+                                 velocity_damping=float(p.velocity_damping))
+        self.body = _Namespace(index={n: i for i, n in enumerate(names)})
+        self.num_bodies = len(names)
+        self.num_joints = 8
+        self.num_joint_dof = 8
+        self.num_forces_dof = 0
+        self._env = env
+
+    def default_angle(self):
+        """System.default_angle(): midpoint of each joint's limit, radians, joint order hip 1, ankle 1, hip 2, ..."""
+        p, out = self._env.params, []
+        for leg in range(4):
+            out.append((p.hip_limit[leg][0] + p.hip_limit[leg][1]) / 2 * math.pi / 180)
+            out.append((p.ank_limit[leg][0] + p.ank_limit[leg][1]) / 2 * math.pi / 180)
+        return torch.tensor(out, dtype=torch.float32, device=self._env.device)
+
+    def __getattr__(self, name):
+        if name in ('step', 'info', 'default_qp', 'joints', 'actuators', 'colliders'):
+            raise AttributeError(f'sys.{name}: the rigid-body pipeline is fused into the CUDA step / reset kernels; '
+                                 'use env.step / env.reset')
+        raise AttributeError(name)
+
+
+class EvalMetrics:
+    """brax.envs.wrappers.EvalMetrics -- the record create(..., eval_metrics=True) puts into
+    state.info['eval_metrics'] (__init__.py:69-70): current_episode_metrics {name: [N]}, completed_episodes_metrics
+    {name: scalar}, completed_episodes, completed_episodes_steps. Plus `.acc` (all 8 device accumulators by name,
+    dev_const.h) with dict-style access (`em['episodes']`, `em.items()`)."""
+    __slots__ = ('current_episode_metrics', 'completed_episodes_metrics', 'completed_episodes',
+                 'completed_episodes_steps', 'acc')
+
+    def __init__(self, current_episode_metrics, completed_episodes_metrics, completed_episodes,
+                 completed_episodes_steps, acc):
+        self.current_episode_metrics, self.completed_episodes_metrics = current_episode_metrics, completed_episodes_metrics
+        self.completed_episodes, self.completed_episodes_steps, self.acc = completed_episodes, completed_episodes_steps, acc
+
+    def items(self):
+        return self.acc.items()
+
+    def __getitem__(self, k):
+        return self.acc[k]
 
 
 class QP:
@@ -46,40 +126,54 @@ class State:
         self.buf = buf
         self._qp = None
         self._cstate = None
+        self._stepped = False      # produced by env.step (not reset / state_from_qp)
+        self._done_bool = None
 
-    # ---- the reference's fields
+    # ---- the reference's fields (an un-vmapped env, create(batch_size=None), has no leading axis)
+    def _x(self, t):
+        return t[0] if self._env.unbatched else t
+
     @property
     def qp(self) -> QP:
         if self._qp is None:
-            self._qp = self._env._unpack(self.buf['qp'], self.buf['aux'])
+            q = self._env._unpack(self.buf['qp'], self.buf['aux'])
+            self._qp = QP(q.pos[0], q.rot[0], q.vel[0], q.ang[0]) if self._env.unbatched else q
         return self._qp
 
     @property
     def obs(self):
-        return self.buf['obs']
+        return self._x(self.buf['obs'])
 
     @property
     def reward(self):
-        return self.buf['reward']
+        return self._x(self.buf['reward'])
 
     @property
     def done(self):
-        return self.buf['done']
+        """f32 0/1 like the reference -- except Tag after a step, where the reference's `done` is a bool
+        (`jp.logical_or(dead, hit)`, ant_tag.py:127; f32 zeros at reset, :88)."""
+        d = self.buf['done']
+        if self._stepped and self._env.env_name == 'ant_tag':
+            if self._done_bool is None:
+                self._done_bool = d != 0
+            d = self._done_bool
+        return self._x(d)
 
     @property
     def metrics(self) -> Dict[str, torch.Tensor]:
-        return self._env._metrics_view(self.buf)
+        m = self._env._metrics_view(self.buf)
+        return {k: v[0] for k, v in m.items()} if self._env.unbatched else m
 
     @property
     def info(self) -> Dict[str, object]:
         b = self.buf
-        info = {'steps': b['steps'], 'truncation': b['truncation']}
+        info = {'steps': self._x(b['steps']), 'truncation': self._x(b['truncation'])}
         if b['rng'] is not None:
-            info['rng'] = b['rng']  # uint32 bit patterns stored as int32 [N, 2]
-        if b['acc'] is not None:  # create(..., eval_metrics=True): device-side episode statistics (brax EvalWrapper's role)
-            info['eval_metrics'] = dict(zip(Env.ACC_NAMES, b['acc'].unbind(0)))
+            info['rng'] = self._x(b['rng'])  # uint32 bit patterns stored as int32 [N, 2]
+        if b['acc'] is not None:  # create(..., eval_metrics=True): brax EvalWrapper's record, kept on the device
+            info['eval_metrics'] = self._env._eval_metrics(b)
         if b['first_qp'] is not None:
-            info['first_obs'] = b['first_obs']
+            info['first_obs'] = self._x(b['first_obs'])
             info['first_qp'] = _LazyQP(self._env, b['first_qp'], b['first_aux'])
         return info
 
@@ -90,13 +184,18 @@ class State:
             if k == 'qp':
                 buf['qp'], buf['aux'] = self._env._pack(v, like_aux=self.buf['aux'])
             elif k in ('obs', 'reward', 'done'):
-                buf[k] = v.to(torch.float32).contiguous()
+                v = v.to(torch.float32)
+                buf[k] = (v.unsqueeze(0) if self._env.unbatched else v).contiguous()
             else:
                 raise TypeError(f'State.replace: unsupported field {k!r}')
-        return State(self._env, buf)
+        out = State(self._env, buf)
+        out._stepped = self._stepped
+        return out
 
     def clone(self):
-        return State(self._env, {k: (None if v is None else v.clone()) for k, v in self.buf.items()})
+        out = State(self._env, {k: (None if v is None else v.clone()) for k, v in self.buf.items()})
+        out._stepped = self._stepped
+        return out
 
     def _c(self):
         if self._cstate is None:
@@ -114,7 +213,8 @@ class _LazyQP:
 
     def _get(self):
         if self._v is None:
-            self._v = self._env._unpack(self._qp, self._aux)
+            q = self._env._unpack(self._qp, self._aux)
+            self._v = QP(q.pos[0], q.rot[0], q.vel[0], q.ang[0]) if self._env.unbatched else q
         return self._v
 
     pos = property(lambda s: s._get().pos)
@@ -161,7 +261,10 @@ class Env:
             raise RuntimeError('po_brax_b200 envs live on a CUDA device')
         if self.device.index is None:
             self.device = torch.device('cuda', torch.cuda.current_device())
-        self.batch_size = 1 if batch_size is None else int(batch_size)
+        # create(batch_size=None) adds no VmapWrapper (__init__.py:64): State fields carry no batch axis. The kernels
+        # always run a batch; an unbatched env is a batch of one whose State strips the axis.
+        self.unbatched = not batch_size
+        self.batch_size = 1 if self.unbatched else int(batch_size)
         if self.batch_size <= 0:
             raise ValueError('`batch_size` must be > 0')
         p = _lib.PobraxParams()
@@ -182,6 +285,16 @@ class Env:
         self.auto_reset = bool(auto_reset)
         self.track_metrics = bool(track_metrics)
         self.episode_length = p.episode_length
+        self.sys = SysShim(self)
+        ix = self.sys.body.index
+        self.torso_idx = ix['$ Torso']
+        for attr, name in (('target_idx', 'Target'), ('hell_idx', 'Hell'), ('priest_idx', 'Priest')):
+            if name in ix:
+                setattr(self, attr, ix[name])
+        if env_name == 'ant_gather':   # ant_gather.py:77-86
+            self.n_apples, self.n_bombs, self.n_bins = p.n_apples, p.n_bombs, p.n_bins
+            self.n_objects = p.n_apples + p.n_bombs
+            self.object_indices = list(range(self.num_bodies - self.n_objects, self.num_bodies))
 
     # ---- constructor kwargs of the reference envs
     def _apply_kwargs(self, p, kw):
@@ -316,6 +429,8 @@ class Env:
             action = torch.as_tensor(np.asarray(action, np.float32))
         if action.device != self.device or action.dtype != torch.float32 or not action.is_contiguous():
             action = action.to(device=self.device, dtype=torch.float32).contiguous()
+        if self.unbatched and action.dim() == 1:
+            action = action.unsqueeze(0)
         if action.shape != (self.batch_size, self.action_size):
             raise ValueError(f'action must have shape ({self.batch_size}, {self.action_size}), got {tuple(action.shape)}')
         # no torch.cuda.device() context here: the library selects the handle's device itself (small batches are
@@ -324,6 +439,7 @@ class Env:
         out = State(self, state.buf)
         out._cstate = state._cstate
         out._action = action
+        out._stepped = True
         return out
 
     def reset_where_done(self, state: State, rng) -> State:
@@ -335,6 +451,7 @@ class Env:
         out = State(self, state.buf)
         out._cstate = state._cstate
         out._keys = keys
+        out._stepped = state._stepped
         return out
 
     def reset_where_done_chain(self, state: State, chain: torch.Tensor) -> State:
@@ -347,6 +464,7 @@ class Env:
                                                           self._stream()), 'pobrax_reset_where_done_chain')
         out = State(self, state.buf)
         out._cstate = state._cstate
+        out._stepped = state._stepped
         return out
 
     def split_keys(self, key, n=None, first=0, count=None) -> torch.Tensor:
@@ -389,10 +507,25 @@ class Env:
             t = getattr(qp, name)
             if not isinstance(t, torch.Tensor):
                 t = torch.as_tensor(np.asarray(t, np.float32))
-            t = t.to(**f).contiguous()
+            t = t.to(**f)
+            if self.unbatched and t.dim() == 2:
+                t = t.unsqueeze(0)
+            t = t.contiguous()
             if t.shape != (n, nb, w):
                 raise ValueError(f'qp.{name} must have shape ({n}, {nb}, {w}), got {tuple(t.shape)}')
             arrs.append(t)
+        if self.env_name == 'ant_heavenhell':
+            # The packed state keeps one flag for the goal side: a QP whose Target / Hell / Priest rows are anything
+            # but the configured positions cannot be represented -- refuse it instead of snapping silently.
+            p = self.params
+            hh = torch.tensor([[p.heaven_hell_xy[i][0], p.heaven_hell_xy[i][1]] for i in range(2)], **f)
+            pr = torch.tensor([p.priest_xy[0], p.priest_xy[1]], **f)
+            tgt, hell = arrs[0][:, self.target_idx, :2], arrs[0][:, self.hell_idx, :2]
+            ok = (((tgt == hh[0]).all(-1) & (hell == hh[1]).all(-1)) | ((tgt == hh[1]).all(-1) & (hell == hh[0]).all(-1))) \
+                & (arrs[0][:, self.priest_idx, :2] == pr).all(-1)
+            if not bool(ok.all()):
+                raise ValueError('ant_heavenhell: qp.pos rows Target / Hell must be the two configured heaven_hell '
+                                 'positions (in either order) and Priest the configured priest_position')
         out = torch.zeros((L.qp_planes, n, 4), **f)
         aux = (like_aux.clone() if like_aux is not None else torch.zeros((L.aux_dim, n), **f)) if L.aux_dim else None
         with torch.cuda.device(self.device):
@@ -424,11 +557,30 @@ class Env:
                     'ant_heavenhell': ('hits',), 'ant_tag': ('hits',), 'ant_gather': ('apples', 'bombs')}
     _METRIC_ZERO = {'ant': (), 'ant_heavenhell': ('heavens', 'hells'), 'ant_tag': (), 'ant_gather': ('objects',)}
 
-    def _metrics_view(self, buf):
-        m = {name: buf['metrics'][i] for i, name in enumerate(self._METRIC_ROWS[self.env_name])}
+    def _metrics_view(self, buf, rows=None):
+        rows = buf['metrics'] if rows is None else rows
+        m = {name: rows[i] for i, name in enumerate(self._METRIC_ROWS[self.env_name])}
         for name in self._METRIC_ZERO[self.env_name]:  # keys the reference creates and never updates
             m[name] = torch.zeros_like(buf['reward'])
         return m
 
+    # which device accumulator holds the sum over completed episodes of each per-step metric (dev_const.h `acc`)
+    _ACC_OF_METRIC = {'ant_heavenhell': {'hits': 4}, 'ant_tag': {'hits': 4}, 'ant_gather': {'apples': 4, 'bombs': 5},
+                      'ant': {}}
+
+    def _eval_metrics(self, buf) -> EvalMetrics:
+        """brax EvalWrapper's record from the device-side accumulators (no per-step host work): per-env running
+        return of the current episode, sums over completed episodes, their count and total length. Unlike brax
+        0.0.12 -- whose current_episode_metrics restart from the terminal step's metrics instead of zero -- an
+        episode's return here is exactly the sum of its own rewards."""
+        acc = buf['acc']
+        done_sums = {'reward': acc[1]}
+        for name, i in self._ACC_OF_METRIC[self.env_name].items():
+            done_sums[name] = acc[i]
+        return EvalMetrics(current_episode_metrics={'reward': buf['ep_return'][0] if self.unbatched else buf['ep_return']},
+                           completed_episodes_metrics=done_sums, completed_episodes=acc[0],
+                           completed_episodes_steps=acc[2], acc=dict(zip(Env.ACC_NAMES, acc.unbind(0))))
+
     ACC_NAMES = ('episodes', 'sum_return', 'sum_length', 'truncations', 'hits_or_apples', 'heavens_or_bombs',
                  'hells', 'dead_steps')
+

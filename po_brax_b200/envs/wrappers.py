@@ -1,7 +1,14 @@
 """Gym-style adapters mirroring /root/reference/po_brax/envs/wrappers.py:126-262 on top of the fused env.
 
 gym itself is not a dependency: the spaces are exposed as plain (low, high, shape) records. Observations,
-rewards and dones are torch CUDA tensors (the reference returns device arrays as well)."""
+rewards and dones are torch CUDA tensors (the reference returns device arrays as well).
+
+Aliasing contract. The fused env updates a State's buffers in place, so the tensors of step t would be overwritten
+by step t + 1. The reference returns fresh immutable arrays every step, and rollout code relies on that
+(`rewards.append(r)`, a `done` read one step late). The gym adapters therefore return COPIES by default
+(`copy=True`: obs, reward, done and the metrics rows are cloned on the device, one small launch each);
+`copy=False` hands out the live buffers for loops that consume a step's outputs before the next step (they are
+then valid until the next `step()` / `reset()`)."""
 from collections import namedtuple
 from typing import Optional
 
@@ -92,12 +99,13 @@ class RandomizedAutoResetWrapperCached(_FunctionalWrapper):
 class VmapGymWrapper:
     """wrappers.py:126-172: batched env behind the gym VectorEnv API; keys = split(key, num_envs + 1)."""
 
-    def __init__(self, env: Env, batch_size: int, seed: int = 0, backend: Optional[str] = None):
+    def __init__(self, env: Env, batch_size: int, seed: int = 0, backend: Optional[str] = None, copy: bool = True):
         if batch_size != env.batch_size:
             raise ValueError('batch_size must equal env.batch_size')
         self._env = env
+        self.copy = copy
         self.metadata = {'render.modes': ['human', 'rgb_array'],
-                         'video.frames_per_second': 1 / (env.params.dt * env.params.action_repeat)}
+                         'video.frames_per_second': 1 / env.sys.config.dt}   # wrappers.py:140
         self.num_envs = batch_size
         self.seed(seed)
         self.backend = backend
@@ -118,15 +126,20 @@ class VmapGymWrapper:
         nxt = prandom.split_at(self._key, n + 1, 0)
         return nxt, keys
 
+    def _out(self, s):
+        """(obs, reward, done, info) of a step: fresh tensors unless copy=False (module docstring)."""
+        if not self.copy:
+            return s.obs, s.reward, s.done, s.metrics
+        return s.obs.clone(), s.reward.clone(), s.done.clone(), self._env._metrics_view(s.buf, s.buf['metrics'].clone())
+
     def reset(self):
         self._key, keys = self._reset_keys()
         self._state = self._env.reset(keys)
-        return self._state.obs
+        return self._state.obs.clone() if self.copy else self._state.obs
 
     def step(self, action):
         self._state = self._env.step(self._state, action)
-        s = self._state
-        return s.obs, s.reward, s.done, s.metrics
+        return self._out(self._state)
 
     @property
     def unwrapped(self):
@@ -143,10 +156,10 @@ class AutoresetVmapGymWrapper(VmapGymWrapper):
     follows the reference literally (`done.any()` on the host, keys drawn by a split launch)."""
 
     def __init__(self, env: Env, batch_size: int, seed: int = 0, backend: Optional[str] = None, sync_free: bool = True,
-                 cuda_graph: bool = False):
+                 cuda_graph: bool = False, copy: bool = True):
         self._chain = None   # int32[4] device tensor (gym key k0, k1, flag, spare) while the key lives on the device
         self._graph = None   # captured (step + reset_where_done_chain) of the current State's buffers
-        super().__init__(env, batch_size, seed, backend)
+        super().__init__(env, batch_size, seed, backend, copy)
         self.sync_free = sync_free
         self.cuda_graph = cuda_graph
 
@@ -196,15 +209,15 @@ class AutoresetVmapGymWrapper(VmapGymWrapper):
                 self._act.copy_(action.reshape(self._act.shape), non_blocking=True)
                 self._graph.replay()
                 self._state = s = self._graph_state
-                return s.obs, s.reward, s.done, s.metrics
+                return self._out(s)
             self._state = s = self._env.step(self._state, action)
             self._state = s = self._env.reset_where_done_chain(s, self._chain)
-            return s.obs, s.reward, s.done, s.metrics
+            return self._out(s)
         self._state = s = self._env.step(self._state, action)
         if bool(s.done.any()):
             self._key, keys = self._reset_keys()
             self._state = s = self._env.reset_where_done(s, keys)
-        return s.obs, s.reward, s.done, s.metrics
+        return self._out(s)
 
 
 class AutoresetGymWrapper:
@@ -212,15 +225,15 @@ class AutoresetGymWrapper:
     reset: key1, key2 = split(key); state = env.reset(key2); key <- key1 (brax GymWrapper.reset). step: when the
     episode ends the env is reset in full from the key chain (fresh info['rng'] too, unlike the batched adapter)
     and the RESET observation is returned together with the finished step's reward / done (`obs` is rebound by the
-    reset in the reference). The fused env is batched, so this wraps a batch of one and
-    strips the batch axis; `if done` is a host decision in the reference too."""
+    reset in the reference). Wraps an un-vmapped env (create(batch_size=None): State fields carry no batch axis);
+    `if done` is a host decision in the reference too. Outputs are copies (module docstring)."""
 
     def __init__(self, env: Env, seed: int = 0, backend: Optional[str] = None):
-        if env.batch_size != 1:
+        if not env.unbatched:
             raise ValueError('AutoresetGymWrapper wraps an unbatched env (create(..., batch_size=None))')
         self._env = env
         self.metadata = {'render.modes': ['human', 'rgb_array'],
-                         'video.frames_per_second': 1 / (env.params.dt * env.params.action_repeat)}
+                         'video.frames_per_second': 1 / env.sys.config.dt}
         self.seed(seed)
         self.backend = backend
         self._state = None
@@ -233,9 +246,9 @@ class AutoresetGymWrapper:
 
     def _reset(self):
         key1, key2 = prandom.split_at(self._key, 2, 0), prandom.split_at(self._key, 2, 1)
-        self._state = self._env.reset(np.array([key2], dtype=np.uint32))
+        self._state = self._env.reset(np.array(key2, dtype=np.uint32))
         self._key = key1
-        return self._state.obs[0]
+        return self._state.obs.clone()
 
     def reset(self):
         return self._reset()
@@ -243,8 +256,8 @@ class AutoresetGymWrapper:
     def step(self, action):
         if not isinstance(action, torch.Tensor):
             action = torch.as_tensor(np.asarray(action, np.float32))
-        self._state = s = self._env.step(self._state, action.reshape(1, -1))
-        obs, reward, done, info = s.obs[0], s.reward[0].clone(), s.done[0].clone(), {k: v[0].clone() for k, v in s.metrics.items()}
+        self._state = s = self._env.step(self._state, action.reshape(-1))
+        obs, reward, done, info = s.obs.clone(), s.reward.clone(), s.done.clone(), {k: v.clone() for k, v in s.metrics.items()}
         if bool(done):
             obs = self._reset()
         return obs, reward, done, info

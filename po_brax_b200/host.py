@@ -31,12 +31,23 @@ class HostStepper:
         self.h2d_bytes_per_step = self.action_host.numel() * 4
         self.d2h_bytes_per_step = (self.obs_host.numel() + self.reward_host.numel() + self.done_host.numel()) * 4
 
+    def _order_after_current(self):
+        """Inputs handed to reset / step may have been produced on the caller's current stream (device keys from
+        shard_keys, an action tensor): every chunk stream first waits for the work enqueued there so far."""
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            st.wait_stream(cur)
+
     def reset(self, keys) -> torch.Tensor:
-        """keys: uint32 [N, 2] (host). Returns the host observation buffer."""
+        """keys: uint32 [N, 2] (host array or device tensor). Returns the host observation buffer."""
+        self._order_after_current()
         for c, (env, st) in enumerate(zip(self.envs, self.streams)):
             sl = slice(c * self.m, (c + 1) * self.m)
             with torch.cuda.stream(st):
-                s = env.reset(keys[sl])
+                k = keys[sl]
+                if isinstance(k, torch.Tensor) and k.is_cuda:
+                    k.record_stream(st)   # allocated on the caller's stream, consumed on this one
+                s = env.reset(k)
                 self.states[c] = s
                 self.obs_host[sl].copy_(s.obs, non_blocking=True)
         self.sync()
@@ -44,6 +55,7 @@ class HostStepper:
 
     def step_async(self):
         """Enqueue: action_host -> device, fused step, obs/reward/done -> host, per chunk on its stream."""
+        self._order_after_current()
         for c, (env, st) in enumerate(zip(self.envs, self.streams)):
             sl = slice(c * self.m, (c + 1) * self.m)
             with torch.cuda.stream(st):

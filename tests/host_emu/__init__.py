@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(HERE, 'emu.cpp')
 OUT = os.path.join(HERE, '_build', 'libpobrax_emu.so')
-DEPS = [SRC] + [os.path.join(ROOT, 'po_brax_b200', 'csrc', f) for f in
+DEPS = [SRC, os.path.join(HERE, 'shim.h')] + [os.path.join(ROOT, 'po_brax_b200', 'csrc', f) for f in
                 ('api.cu', 'ant_physics.cuh', 'vec.cuh', 'dev_const.h', 'threefry.cuh')] + \
        [os.path.join(ROOT, 'include', 'pobrax.h')]
 CUDA = os.environ.get('CUDA_HOME', '/usr/local/cuda')

@@ -13,7 +13,8 @@
 //    partner lane recorded for the same call in the previous pass, and passes repeat until no recorded value
 //    changes (3 passes for a two-round butterfly).
 //  * tex2DLayered -> the host copy of the candidate tables (C.wall_tex holds its address), __ldg -> a load,
-//    the f32x2 PTX -> the same operation per half (vec.cuh / ant_physics.cuh, POBRAX_HOST_EMU branches).
+//    the f32x2 PTX -> the same operation per half: tests/host_emu/shim.h, included ahead of the product headers
+//    (which only skip their own PTX / MUFU / texture definitions under POBRAX_HOST_EMU).
 //  * DevConst comes from the product's own host code: api.cu is compiled in as host C++ (its launch_* entry points
 //    are stubbed: nothing here can launch a kernel).
 #define POBRAX_HOST_EMU 1
@@ -42,6 +43,7 @@ cudaError_t launch_pack(const DevConst&, const float*, const float*, const float
 cudaError_t launch_split_keys(const uint32_t*, int, int, int, uint32_t*, cudaStream_t) { return cudaErrorNotSupported; }
 cudaError_t launch_fma_probe(float*, int, int, cudaStream_t) { return cudaErrorNotSupported; }
 cudaError_t launch_split_pairs(const uint32_t*, int, uint32_t*, uint32_t*, cudaStream_t) { return cudaErrorNotSupported; }
+cudaError_t setup_device(DevConst&, size_t, const char** what) { *what = "host emulator"; return cudaErrorNotSupported; }
 }  // namespace pobrax
 
 // ---- device intrinsics the physics header uses
@@ -66,6 +68,7 @@ static inline float __shfl_xor_sync(unsigned, float v, int m) {
   return q.prev[c][q.lane ^ m];
 }
 
+#include "shim.h"                                // host stand-ins for the PTX / MUFU / texture primitives
 #include "../../po_brax_b200/csrc/ant_physics.cuh"
 
 namespace {

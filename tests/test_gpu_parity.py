@@ -646,10 +646,29 @@ def test_ragged_and_tiny_batches():
             for _ in range(3):
                 sb, ss = big.step(sb, a), small.step(ss, a[:n].contiguous())
             assert torch.equal(sb.obs[:n], ss.obs) and torch.equal(sb.buf['qp'][:, :n], ss.buf['qp'])
+
+
+def test_unvmapped_create_has_no_batch_axis():
+    """create(batch_size=None) adds no VmapWrapper (__init__.py:64): reset takes one key, State fields carry no batch
+    axis -- obs (D,), scalar reward / done, qp.pos (nb, 3) -- and equal env 0 of a batch built from the same key."""
     from po_brax_b200 import envs
-    one = envs.create('ant_tag')  # batch_size None -> a single env
-    s = one.reset(P.keys_for(1))
-    assert tuple(s.obs.shape) == (1, 103)
+    for kind in KINDS:
+        one = envs.create(kind, auto_reset=False)
+        key = P.keys_for(1)[0]
+        s = one.reset(key)
+        ref_env = _make(kind, 1, auto_reset=False)
+        r = ref_env.reset(key[None])
+        D, nb = one.observation_size, one.num_bodies
+        assert tuple(s.obs.shape) == (D,) and s.reward.dim() == 0 and s.done.dim() == 0
+        assert tuple(s.qp.pos.shape) == (nb, 3) and tuple(s.qp.rot.shape) == (nb, 4)
+        assert all(v.dim() == 0 for v in s.metrics.values()) and s.info['steps'].dim() == 0
+        if kind != 'ant':
+            assert tuple(s.info['rng'].shape) == (2,)
+        a = torch.full((8,), 0.25, device='cuda')
+        s, r = one.step(s, a), ref_env.step(r, a[None])
+        assert torch.equal(s.obs, r.obs[0]) and torch.equal(s.reward, r.reward[0]) and torch.equal(s.qp.pos, r.qp.pos[0])
+        s2 = s.replace(obs=torch.zeros(D, device='cuda'))
+        assert tuple(s2.obs.shape) == (D,)
 
 
 def test_eval_metrics_accumulators_match_a_host_recount():
@@ -731,9 +750,9 @@ def test_unbatched_gym_env_follows_the_brax_gym_key_chain():
     ks2 = tf.split(ks[0], 2)
     want2 = oenv.reset(ks2[1:2])
     assert np.allclose(P.t2n(o)[cols], want2.obs[0, cols], atol=2e-5)
-    assert (P.rng_bits(e._state.info['rng']) == want2.info['rng']).all()   # full reset: fresh info['rng']
+    assert (P.rng_bits(e._state.info['rng']) == want2.info['rng'][0]).all()   # full reset: fresh info['rng']
     assert list(e._key) == ks2[0].tolist()
-    assert float(e._state.info['steps'][0]) == 0.0 and float(e._state.done[0]) == 0.0
+    assert float(e._state.info['steps']) == 0.0 and float(e._state.done) == 0.0
     with pytest.raises(ValueError):
         envs.create_gym_env('ant_tag', batch_size=0)
 
@@ -765,3 +784,199 @@ def test_gym_step_as_cuda_graph_equals_plain_launches(kind):
     assert len(outs[0]) == len(outs[1])
     for i, (a, b) in enumerate(zip(*outs)):
         assert torch.equal(a, b), (kind, i)
+
+
+def test_gym_outputs_of_step_t_survive_step_t_plus_1():
+    """The reference returns fresh arrays every step; rollout code keeps them (`dones.append(d)`). The gym adapters
+    return copies by default; copy=False hands out the live buffers (valid until the next step)."""
+    from po_brax_b200 import envs
+    n = 64
+    for graph in (False, True):
+        e = envs.create_gym_env('ant_tag', batch_size=n, seed=3, episode_length=3, cuda_graph=graph)
+        obs0 = e.reset()
+        keep0 = obs0.clone()
+        g = torch.Generator(device='cuda').manual_seed(5)
+        held, snaps = [], []
+        for t in range(5):
+            out = e.step(torch.rand((n, 8), device='cuda', generator=g) * 2 - 1)
+            held.append(out)
+            snaps.append((out[0].clone(), out[1].clone(), out[2].clone(), {k: v.clone() for k, v in out[3].items()}))
+        assert torch.equal(obs0, keep0)
+        for (o, r, d, m), (so, sr, sd, sm) in zip(held, snaps):
+            assert torch.equal(o, so) and torch.equal(r, sr) and torch.equal(d, sd)
+            assert all(torch.equal(m[k], sm[k]) for k in m)
+        assert any(bool(d.any()) for _, _, d, _ in held) and not bool(held[0][2].all())   # dones differ over the steps
+    live = envs.create_gym_env('ant_tag', batch_size=n, seed=3, episode_length=3, copy=False)
+    live.reset()
+    o1 = live.step(torch.zeros((n, 8), device='cuda'))[0]
+    assert o1.data_ptr() == live._state.buf['obs'].data_ptr()
+
+
+def test_tag_done_is_bool_after_a_step():
+    """ant_tag.py:88 vs :127: done is f32 zeros at reset and `jp.logical_or(dead, hit)` (bool) after a step; the
+    other envs stay f32."""
+    for kind in KINDS:
+        env = _make(kind, 16, auto_reset=False)
+        s = env.reset(P.keys_for(16))
+        assert s.done.dtype == torch.float32
+        s = env.step(s, torch.zeros((16, 8), device='cuda'))
+        assert s.done.dtype == (torch.bool if kind == 'ant_tag' else torch.float32)
+        assert torch.equal(s.done.float(), s.buf['done'])
+
+
+def test_env_sys_surface():
+    """What code outside the envs reads from env.sys (wrappers.py:22-23,140; ant_heavenhell.py:64-69,90)."""
+    from oracle import config as ocfg
+    for kind, cfg in (('ant', ocfg.ant_config()), ('ant_heavenhell', None), ('ant_tag', None), ('ant_gather', None)):
+        env = _make(kind, 4, action_repeat=2)
+        o = oenvs.ENVS[kind](action_repeat=2)
+        assert env.sys.num_bodies == o.sys.num_bodies == env.num_bodies
+        assert env.sys.body.index == o.sys.index
+        assert env.sys.num_joint_dof == 8 and env.action_size == env.sys.num_joint_dof + env.sys.num_forces_dof
+        assert abs(env.sys.config.dt - 0.1) < 1e-7 and env.sys.config.substeps == 20
+        assert np.allclose(P.t2n(env.sys.default_angle()), o.sys.default_angle(), atol=1e-7)
+        assert env.torso_idx == o.torso_idx
+        for name in ('target_idx', 'hell_idx', 'priest_idx'):
+            if hasattr(o, name):
+                assert getattr(env, name) == getattr(o, name)
+        with pytest.raises(AttributeError):
+            env.sys.step
+
+
+def test_eval_metrics_record_has_the_brax_shape():
+    """create(eval_metrics=True) -> state.info['eval_metrics'] is an EvalMetrics record (brax EvalWrapper): per-env
+    current return, completed sums, episode count and total steps."""
+    n, L = 256, 6
+    env = _make('ant_tag', n, episode_length=L, auto_reset=True, eval_metrics=True)
+    s = env.reset(P.keys_for(n, seed=2))
+    g = torch.Generator(device='cuda').manual_seed(9)
+    cur = torch.zeros(n, device='cuda')
+    done_sum = episodes = steps = hits = 0.0
+    for t in range(20):
+        s = env.step(s, torch.rand((n, 8), device='cuda', generator=g) * 2 - 1)
+        cur += s.reward
+        d = s.done
+        done_sum += float(cur[d].double().sum()); episodes += float(d.sum()); steps += float(s.info['steps'][d].sum())
+        hits += float(s.metrics['hits'].sum())
+        cur[d] = 0
+    em = s.info['eval_metrics']
+    assert tuple(em.current_episode_metrics['reward'].shape) == (n,)
+    assert torch.allclose(em.current_episode_metrics['reward'], cur, atol=1e-6)
+    assert float(em.completed_episodes) == episodes and float(em.completed_episodes_steps) == steps
+    assert abs(float(em.completed_episodes_metrics['reward']) - done_sum) < 1e-6
+    assert float(em.completed_episodes_metrics['hits']) == hits
+    assert em['episodes'] is em.acc['episodes']
+
+
+def test_heavenhell_pack_refuses_unrepresentable_goal_rows():
+    """State.replace(qp=...) / state_from_qp: the packed state keeps one goal-side flag, so Target / Hell / Priest
+    rows other than the configured positions raise instead of snapping silently."""
+    env = _make('ant_heavenhell', 8, auto_reset=False)
+    s = env.reset(P.keys_for(8))
+    q = s.qp
+    s2 = s.replace(qp=q)                                   # the unpacked qp round-trips
+    assert torch.equal(s2.buf['aux'], s.buf['aux'])
+    swapped = q.pos.clone()
+    swapped[:, [env.target_idx, env.hell_idx]] = swapped[:, [env.hell_idx, env.target_idx]]
+    s3 = s.replace(qp=q.replace(pos=swapped))              # the other side is representable
+    assert torch.equal(s3.buf['aux'][2], 1.0 - s.buf['aux'][2])
+    bad = q.pos.clone()
+    bad[3, env.target_idx, 0] += 1e-3
+    with pytest.raises(ValueError):
+        s.replace(qp=q.replace(pos=bad))
+    bad = q.pos.clone()
+    bad[0, env.priest_idx, 1] = 6.5
+    with pytest.raises(ValueError):
+        env.state_from_qp(q.replace(pos=bad))
+
+
+def test_gather_fractional_cage_keeps_the_reference_grid():
+    """ant_gather.py:88: arange(-cage, cage + 1) keeps a fractional origin (cage 4.5 -> -4.5 ... 4.5); object
+    placement, the waiting area and the walls must match the oracle built with the same cage."""
+    n = 128
+    kw = dict(cage_xy=(4.5, 3.5), n_apples=4, n_bombs=3)
+    oenv = oenvs.ENVS['ant_gather'](**kw)
+    env = _make('ant_gather', n, auto_reset=False, **kw)
+    keys = P.keys_for(n, seed=13)
+    s, cs = oenv.reset(keys), env.reset(keys)
+    assert np.array_equal(P.t2n(cs.qp.pos)[:, oenv.obj], s.qp.pos[:, oenv.obj])
+    assert (np.abs(s.qp.pos[:, oenv.obj, 0]) % 1 == 0.5).all()
+    # walk the objects into the waiting area: done-if-all-collected compares against the same waiting position
+    far = s.qp.pos.copy()
+    far[:, oenv.obj] = oenv.waiting_area
+    far[0, oenv.obj[0]] = s.qp.pos[0, oenv.obj[0]]
+    from oracle import brax_v1 as bx
+    qp = bx.QP(far, s.qp.rot, s.qp.vel, s.qp.ang)
+    nxt = oenv.step(oenvs.State(qp.copy(), s.obs, s.reward, s.done, dict(s.metrics), dict(s.info)), np.zeros((n, 8), np.float32))
+    got = env.step(env.state_from_qp(P.qp_to_torch(qp), rng=s.info['rng']), torch.zeros((n, 8), device='cuda'))
+    assert np.array_equal(P.t2n(got.done), nxt.done) and nxt.done[1:].all() and not nxt.done[0]
+
+
+def test_raw_c_abi_without_the_facade():
+    """pobrax_create / reset / step / unpack_qp / destroy driven straight through ctypes on caller-owned device
+    buffers (torch only allocates them): what a reference-side binding would do."""
+    import ctypes as C
+    from po_brax_b200 import _lib
+    lib = C.CDLL(_lib.LIB_PATH)
+    n = 96
+    p = _lib.PobraxParams()
+    assert lib.pobrax_default_params(_lib.ANT_HEAVENHELL, C.byref(p)) == 0
+    p.num_envs, p.auto_reset = n, _lib.AUTORESET_OFF
+    L = _lib.PobraxLayout()
+    assert lib.pobrax_layout(C.byref(p), C.byref(L)) == 0
+    h = C.c_void_p()
+    assert lib.pobrax_create(C.byref(p), 0, C.byref(h)) == 0
+    f = dict(dtype=torch.float32, device='cuda:0')
+    buf = {'qp': torch.zeros((L.qp_planes, n, 4), **f), 'aux': torch.zeros((L.aux_dim, n), **f),
+           'obs': torch.zeros((n, L.obs_dim), **f), 'reward': torch.zeros(n, **f), 'done': torch.zeros(n, **f),
+           'steps': torch.zeros(n, **f), 'truncation': torch.zeros(n, **f),
+           'rng': torch.zeros((n, 2), dtype=torch.int32, device='cuda:0'), 'metrics': torch.zeros((L.metrics_dim, n), **f)}
+    st = _lib.PobraxState()
+    for k, v in buf.items():
+        setattr(st, k, v.data_ptr())
+    keys_np = P.keys_for(n, seed=0)
+    keys = torch.from_numpy(keys_np.view(np.int32).copy()).cuda()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    lib.pobrax_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pobrax_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pobrax_unpack_qp.argtypes = [C.c_void_p] * 8
+    lib.pobrax_last_error.restype = C.c_char_p
+    assert lib.pobrax_reset(h, keys.data_ptr(), C.byref(st), stream) == 0, lib.pobrax_last_error()
+    a_np = tf.uniform(tf.prng_key(1), n * 8, -1.0, 1.0).reshape(n, 8)
+    act = torch.from_numpy(a_np).cuda()
+    assert lib.pobrax_step(h, C.byref(st), act.data_ptr(), stream) == 0, lib.pobrax_last_error()
+    nb = L.num_bodies
+    pos, rot = torch.empty((n, nb, 3), **f), torch.empty((n, nb, 4), **f)
+    vel, ang = torch.empty((n, nb, 3), **f), torch.empty((n, nb, 3), **f)
+    assert lib.pobrax_unpack_qp(h, buf['qp'].data_ptr(), buf['aux'].data_ptr(), pos.data_ptr(), rot.data_ptr(),
+                                vel.data_ptr(), ang.data_ptr(), stream) == 0
+    torch.cuda.synchronize()
+    oenv = oenvs.AntHeavenHellEnv()
+    o = oenv.step(oenv.reset(keys_np), a_np)
+    assert (buf['rng'].cpu().numpy().view(np.uint32) == o.info['rng']).all()
+    assert np.array_equal(buf['done'].cpu().numpy(), o.done) and np.array_equal(buf['reward'].cpu().numpy(), o.reward)
+    assert np.abs(pos.cpu().numpy() - o.qp.pos).max() < 1e-4 and np.abs(rot.cpu().numpy() - o.qp.rot).max() < 1e-4
+    assert np.array_equal(pos.cpu().numpy()[:, 9:], o.qp.pos[:, 9:])
+    # errors come back as codes + a message, never as a crash
+    assert lib.pobrax_step(h, C.byref(st), None, stream) != 0 and b'null' in lib.pobrax_last_error()
+    assert lib.pobrax_destroy(h) == 0
+
+
+def test_two_handles_on_two_devices():
+    """One process driving two GPUs: kernel attributes / occupancy are set up per handle on its own device
+    (Gather's reset needs > 48 KB of dynamic shared memory from cage_xy 7 on)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    from po_brax_b200 import envs
+    n, kw = 256, dict(cage_xy=(8, 8))
+    outs = []
+    for dev in (0, 1):
+        env = envs.Env('ant_gather', batch_size=n, device=f'cuda:{dev}', **kw)
+        keys = P.keys_for(n, seed=4)
+        s = env.reset(keys)
+        a = torch.full((n, 8), 0.1, device=f'cuda:{dev}')
+        for _ in range(3):
+            s = env.step(s, a)
+        torch.cuda.synchronize(dev)
+        outs.append((s.obs.cpu(), s.buf['qp'].cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])

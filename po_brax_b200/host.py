@@ -5,11 +5,47 @@ rewards / dones wanted back in host memory), as the reference's gym adapters do 
 The batch is split into independent sub-batches (envs never interact, so this is exact -- see the
 shard-equivalence test), each with its own stream, so the host->device copy of chunk c+1 overlaps the
 step kernel of chunk c and the device->host copy of chunk c-1."""
-from typing import List
+import os
+from typing import List, Optional
 
 import torch
 
 from .envs.env import Env
+
+
+def _gpu_numa_node(index: int) -> Optional[int]:
+    """NUMA node of CUDA device `index` from sysfs (None when the platform does not say: containers often report -1)."""
+    try:
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(index), 'pci_domain_id', 0)
+        dev = getattr(torch.cuda.get_device_properties(index), 'pci_device_id', 0)
+        path = f'/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node'
+        node = int(open(path).read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa_node(index: int) -> dict:
+    """One process per GPU: restrict this process to the CPUs of its GPU's NUMA node BEFORE the pinned host buffers
+    are allocated, so first touch puts them next to the PCIe root the GPU hangs off (8 ranks pinning memory wherever
+    the allocator lands send half of the device->host traffic across the socket interconnect). Best effort: returns
+    what was done ({'node': ..., 'cpus': n} or {'node': None, 'why': ...}); never raises."""
+    node = _gpu_numa_node(index)
+    if node is None:
+        return {'node': None, 'why': 'sysfs reports no NUMA node for the GPU'}
+    try:
+        cpus = set()
+        for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {'node': node, 'why': 'no allowed CPU on that node'}
+        os.sched_setaffinity(0, cpus)
+        return {'node': node, 'cpus': len(cpus)}
+    except Exception as e:   # noqa: BLE001
+        return {'node': node, 'why': f'{type(e).__name__}: {e}'}
 
 
 class HostStepper:

@@ -220,6 +220,15 @@ static void FN(contacts)(const FN(SysDesc) *S, const REAL *pos, const REAL *rot,
                 /* a segment point inside the box: dvec = 0 exactly => n = 0, nv = 0 and no impulse in any evaluation
                  * order: not rounding-ambiguous, kept out of the margin / branch bookkeeping */
                 const int degenerate = dist == (REAL)0;
+                if (mg) {   /* ... but AT the surface the normal swings from 0 to unit length within ~1e-5 m: a closest
+                             * point that close to a box face is rounding-ambiguous although no predicate switches
+                             * (brax_v1._wall_contacts `surface`) */
+                    double depth = 1e9, sf;
+                    for (int i = 0; i < 3; i++) depth = fmin(depth, fmin((double)(sp[i] - lo[i]), (double)(hi[i] - sp[i])));
+                    sf = dist > 0 ? (double)dist * 10.0 : (depth >= 0 ? depth * 100.0 : 1e9);
+                    *mg = fmin(*mg, sf);
+                    if (bc && sf < bc->cause[4]) bc->cause[4] = sf;
+                }
                 FN(impulse)(S, b, p, bp, cvel, n, pen, dv, da, degenerate ? 0 : mg, degenerate ? 0 : bc, 1);
                 cnt[b] += (dv[0] != 0 || dv[1] != 0 || dv[2] != 0) ? (REAL)1 : (REAL)0;
                 for (int i = 0; i < 3; i++) { sv[b][i] += dv[i]; sa[b][i] += da[i]; }

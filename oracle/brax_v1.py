@@ -341,10 +341,11 @@ class System:
         return dvel, dangs + adang
 
     # ------------------------------------------------------------------ contacts
-    def _impulse(self, qp_pos, body, cpos, cvel, normal, pen, degenerate=None):
+    def _impulse(self, qp_pos, body, cpos, cvel, normal, pen, degenerate=None, surface=None):
         """OneWayCollider._contact. All [N,K,...]; body = body index per K.
         degenerate [N,K] (test aid only): contacts whose normal is exactly the zero vector -- nv = J-part = 0 exactly
-        in any evaluation order, so they are not rounding-ambiguous and stay out of the margin bookkeeping."""
+        in any evaluation order, so they are not rounding-ambiguous and stay out of the margin bookkeeping.
+        surface [N,K] (test aid only): an extra margin per contact (see _wall_contacts)."""
         zero, one = self.dtype(0), self.dtype(1)
         inv_m = (one / self.mass[body])
         inv_i = self.inv_inertia[body]
@@ -368,12 +369,12 @@ class System:
         apply_n = np.where((pen > zero) & (nv < zero) & (J > zero), one, zero)
         apply_d = apply_n * np.where(nd > self.dtype(0.01), one, zero)
         if self.track_margin:
-            self._note_margin(pen, nv, J, nd, degenerate)
+            self._note_margin(pen, nv, J, nd, degenerate, surface)
         dvel = dpn_vel * apply_n[..., None] + dpd_vel * apply_d[..., None]
         dang = dpn_ang * apply_n[..., None] + dpd_ang * apply_d[..., None]
         return dvel.astype(self.dtype), dang.astype(self.dtype)
 
-    def _note_margin(self, pen, nv, J, nd, degenerate=None):
+    def _note_margin(self, pen, nv, J, nd, degenerate=None, surface=None):
         """Test aid: distance of each contact from its nearest discontinuous branch (pen > 0, nv < 0, J > 0,
         |v_d| > 0.01; the actuator cut-off at the joint limits is noted in _joints_and_actuators). An env whose margin is ~1 ulp may legitimately take the other branch in a different
         float32 evaluation order (the reference's XLA program included); parity tests skip those envs."""
@@ -386,6 +387,8 @@ class System:
         m = np.minimum(m, np.where(live & (nv < 0) & (J > 0), np.abs(nd - 0.01), big))
         if degenerate is not None:
             m = np.where(degenerate, big, m)
+        if surface is not None:
+            m = np.minimum(m, surface)
         m = m.min(axis=-1)
         self.margin = m if self.margin is None else np.minimum(self.margin, m)
 
@@ -475,7 +478,14 @@ class System:
         pen = rad - dist
         cvel = vel + cross(ang, box_p - pos)
         # a segment point inside the box: dvec = 0 exactly => n = 0, nv = 0, no impulse, in any evaluation order
-        dvel, dang = self._impulse(pos, b, box_p, cvel, n, pen, degenerate=(dist == 0))
+        surface = None
+        if self.track_margin:
+            # ... but AT the surface the normal dvec / (1e-6 + dist) swings from 0 to unit length within ~1e-5 m: a
+            # closest point that close to a box face (outside: dist < 5e-5; inside: depth < 5e-6) is rounding-
+            # ambiguous although no predicate switches. Margin in the units of _note_margin.
+            depth = np.minimum(seg_p - lo, hi - seg_p).min(axis=-1).astype(np.float64)
+            surface = np.where(dist > 0, dist.astype(np.float64) * 10.0, np.where(depth >= 0, depth * 100.0, 1e9))
+        dvel, dang = self._impulse(pos, b, box_p, cvel, n, pen, degenerate=(dist == 0), surface=surface)
         return self._group_reduce(N, b, dvel, dang)
 
     def _contacts(self, qp: QP):

@@ -127,7 +127,6 @@ class State:
         self._qp = None
         self._cstate = None
         self._stepped = False      # produced by env.step (not reset / state_from_qp)
-        self._done_bool = None
 
     # ---- the reference's fields (an un-vmapped env, create(batch_size=None), has no leading axis)
     def _x(self, t):
@@ -154,9 +153,7 @@ class State:
         (`jp.logical_or(dead, hit)`, ant_tag.py:127; f32 zeros at reset, :88)."""
         d = self.buf['done']
         if self._stepped and self._env.env_name == 'ant_tag':
-            if self._done_bool is None:
-                self._done_bool = d != 0
-            d = self._done_bool
+            d = d != 0    # a fresh tensor on every access: the buffer is updated in place by later steps
         return self._x(d)
 
     @property
@@ -263,10 +260,10 @@ class Env:
             self.device = torch.device('cuda', torch.cuda.current_device())
         # create(batch_size=None) adds no VmapWrapper (__init__.py:64): State fields carry no batch axis. The kernels
         # always run a batch; an unbatched env is a batch of one whose State strips the axis.
-        self.unbatched = not batch_size
+        self.unbatched = not batch_size    # `if batch_size:` in the reference: None and 0 both mean un-vmapped
         self.batch_size = 1 if self.unbatched else int(batch_size)
         if self.batch_size <= 0:
-            raise ValueError('`batch_size` must be > 0')
+            raise ValueError('`batch_size` must be None or a positive integer')
         p = _lib.PobraxParams()
         _lib.check(self.lib.pobrax_default_params(KINDS[env_name], C.byref(p)), 'pobrax_default_params')
         p.num_envs = self.batch_size

@@ -430,7 +430,8 @@ def test_shard_equivalence_and_invariants():
 def test_errors_are_loud():
     from po_brax_b200 import envs
     with pytest.raises(ValueError):
-        envs.create('ant', batch_size=0)
+        envs.create('ant', batch_size=-2)
+    assert envs.create('ant', batch_size=0).unbatched     # __init__.py:64 `if batch_size:` -- 0 means un-vmapped too
     with pytest.raises(KeyError):
         envs.create('humanoid', batch_size=4)
     env = envs.create('ant_tag', batch_size=4)

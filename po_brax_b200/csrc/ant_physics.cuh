@@ -178,6 +178,16 @@ __device__ __forceinline__ unsigned wall_mask_at(const DevConst& C, int kind, fl
   return tex2DLayered<unsigned char>((cudaTextureObject_t)C.wall_tex, fmaf(x, C.sdf_inv_cell, C.sdf_bx),
                                      fmaf(y, C.sdf_inv_cell, C.sdf_by), kind);
 }
+// Candidate walls of a lower-leg capsule END (tip or knee, a sphere of radius r_leg centred at (x, y)): bit w set <=>
+// the cell is within r_leg of wall w's footprint, or within half the capsule's segment + r_leg of one of its four
+// footprint vertices. That makes the two end lookups together exact for the whole capsule: against a flat face the
+// distance along the segment is linear (smallest at an end), so an interior point can only be closest next to a
+// vertex, and then the end nearer to it is within half a segment of that vertex. Own table at 1/32 m cells -- the
+// band along a face is r_leg wide, not the capsule's reach -- read through a 2D texture like the body tables.
+__device__ __forceinline__ unsigned tip_mask_at(const DevConst& C, float x, float y) {
+  return tex2D<unsigned char>((cudaTextureObject_t)C.tip_tex, fmaf(x, C.tip_inv_cell, C.tip_bx),
+                              fmaf(y, C.tip_inv_cell, C.tip_by));
+}
 #endif
 
 // Per-lane constants of leg l.
@@ -283,56 +293,56 @@ __device__ __forceinline__ bool wall_far_single(const Body& b, V3 e, float rad, 
   return box_out_of_reach(b, e, rad, mk(l4.x, l4.y, l4.z), mk(h4.x, h4.y, h4.z));
 }
 
-// A multi-candidate mask (cells near a corner) reduced to the boxes that are exactly within reach: ants that the
-// walls funnel into corners keep two candidates for many steps, but a leg is rarely within reach of both, so
-// the survivor usually takes the single-box inline path (converged with the warp's other flagged lanes) instead of
-// the out-of-line group. Out of line itself: multi-candidate lanes are rare, the loop must not grow the substep.
-__device__ __noinline__ unsigned cull_multi(V3 p, V3 e, float rad, unsigned m, const float4* __restrict__ walls) {
-  unsigned keep = 0u;
-  const float ex = fabsf(e.x), ey = fabsf(e.y), ez = fabsf(e.z), rs = rad + 1e-5f;
-  do {
-    const int k = __ffs(m) - 1;
-    m &= m - 1u;
-    const float4 lo = __ldg(walls + 2 * k), hi = __ldg(walls + 2 * k + 1);
-    const float gap = fmaxf(fmaxf(fmaxf(lo.x - (p.x + ex), (p.x - ex) - hi.x), fmaxf(lo.y - (p.y + ey), (p.y - ey) - hi.y)),
-                            fmaxf(lo.z - (p.z + ez), (p.z - ez) - hi.z));
-    if (!(gap > rs)) keep |= 1u << k;
-  } while (m);
-  return keep;
-}
-__device__ __forceinline__ unsigned cull_candidates(const Body& b, V3 e, float rad, unsigned m, const DevConst& C) {
-  return (m & (m - 1u)) ? cull_multi(b.p, e, rad, m, C.walls) : m;
+// One-way contact impulse for a HORIZONTAL normal n = (nx, ny, 0): `impulse` with the zero terms dropped.
+__device__ __forceinline__ Imp impulse_planar(V3 rel, V3 v, float nx, float ny, float pen, float inv_m, float baumgarte,
+                                              float friction, float elasticity) {
+  Imp o;
+  o.dv = o.dw = mk(0.f, 0.f, 0.f);
+  o.hit = 0.0f;
+  const float nv = nx * v.x + ny * v.y;
+  const V3 t1 = mk(-rel.z * ny, rel.z * nx, rel.x * ny - rel.y * nx);   // rel x n
+  const float rden = rcp_ftz(inv_m + dot(t1, t1));                       // n.((rel x n) x rel) = |rel x n|^2
+  const float J = (baumgarte * pen - (1.0f + elasticity) * nv) * rden;
+  if (!((pen > 0.0f) && (nv < 0.0f) && (J > 0.0f))) return o;
+  o.dv = mk(inv_m * (J * nx), inv_m * (J * ny), 0.f);
+  o.dw = J * t1;
+  const V3 vd = mk(v.x - nv * nx, v.y - nv * ny, v.z);
+  const float nd = sqrt_pos(dot(vd, vd));
+  if (nd > 0.01f) {
+    const float Jd = fminf(nd * rden, friction * J);
+    const V3 Jdv = (-Jd * rcp_ftz(1e-6f + nd)) * vd;
+    o.dv += inv_m * Jdv;
+    o.dw += cross(rel, Jdv);
+  }
+  o.hit = 1.0f;
+  return o;
 }
 
-// Inline fast path of a body's Arena group for the common case -- ONE candidate box and the closest segment point
-// at an end (g(0) >= 0 or g(1) <= 0 in seg_box_t, i.e. no bisection): same arithmetic as contact_general, but
-// from the constant bank and without the call. Returns false when the out-of-line group has to run instead.
-__device__ __forceinline__ bool wall_single(const Body& b, V3 e, float rad, float inv_m, unsigned m, const DevConst& C,
-                                            Imp& c) {
+// Inline fast path of the lower leg's Arena group for what wall contacts are in practice (98-100 % of them over an
+// episode, tools/wall_stats.py): the capsule's TIP (its t = 0 end, F = p + e) against the flat side of ONE box. Applies
+// when the two end lookups name a single candidate box, the tip's closest box point lies in the tip's own height
+// (dz = 0: the normal is horizontal, side face or vertical edge) and the tip is the capsule's closest point
+// (g(0) >= 0 in seg_box_t <=> d.e <= 0). Same arithmetic as contact_general + impulse with the zero terms dropped.
+// Returns false when the out-of-line group has to run instead (two candidates, top / bottom of the wall involved,
+// knee or interior point closest).
+__device__ __forceinline__ bool tip_wall(const Body& b, V3 e, float rad, float inv_m, unsigned m, const DevConst& C,
+                                         Imp& c) {
   if (m & (m - 1u)) return false;
   const int k = __ffs(m) - 1;
   const float4 l4 = C.wall_box[k][0], h4 = C.wall_box[k][1];
-  const V3 lo = mk(l4.x, l4.y, l4.z), hi = mk(h4.x, h4.y, h4.z);
+  const V3 F = b.p + e;
+  const V3 bp = clamp3(F, mk(l4.x, l4.y, l4.z), mk(h4.x, h4.y, h4.z));
+  const float dx = F.x - bp.x, dy = F.y - bp.y;
+  if (F.z != bp.z || dx * e.x + dy * e.y > 0.0f) return false;
   c.dv = c.dw = mk(0.f, 0.f, 0.f);
   c.hit = 0.0f;
-  if (box_out_of_reach(b, e, rad, lo, hi)) return true;
-  const V3 a = b.p + e;
-  const V3 d = (b.p - e) - a;
-  const V3 p1 = a + d;  // g(1) is evaluated at a + 1*d, as in seg_box_t
-  const V3 ca = clamp3(a, lo, hi), cb = clamp3(p1, lo, hi);
-  const V3 da = a - ca, db = p1 - cb;
-  const bool t0 = dot(da, d) >= 0.0f;
-  if (!t0 && !(dot(db, d) <= 0.0f)) return false;  // interior minimum: bisection, out of line
-  const V3 dvec = t0 ? da : db, bp = t0 ? ca : cb;
-  const float d2 = dot(dvec, dvec), rs = rad + 1e-6f;
+  const float d2 = dx * dx + dy * dy, rs = rad + 1e-6f;
   if (d2 < rs * rs) {
     const float dist = sqrt_pos(d2);
     const float pen = rad - dist;
-    if (pen > 0.0f) {
-      const V3 n = rcp_ftz(1e-6f + dist) * dvec;
-      const V3 rel = bp - b.p;
-      c = impulse(rel, b.v + cross(b.w, rel), n, pen, inv_m, C.baumgarte, C.friction, C.elasticity);
-    }
+    const float inv = rcp_ftz(1e-6f + dist);
+    const V3 rel = bp - b.p;
+    c = impulse_planar(rel, b.v + cross(b.w, rel), inv * dx, inv * dy, pen, inv_m, C.baumgarte, C.friction, C.elasticity);
   }
   return true;
 }
@@ -447,7 +457,7 @@ __device__ __forceinline__ F2 limit_and_actuator2(F2 sin_psi, F2 cos_psi, F2 lim
 // group's "divide by the active count" is a no-op; the wall group divides per body.
 template <bool WALLS>
 __device__ __forceinline__ void contacts2(Rig2& r, const DevConst& C, V3 dA, V3 dB, unsigned mT, unsigned mA,
-                                          unsigned mB, int leg, ContactAcc& acc) {
+                                          unsigned mB, int leg, ContactAcc& acc) {   // mB: tip | knee end lookups
   Body A, B;  // scalar views of the two halves (only v / w are written back)
   A.p = lo3(r.L.p); A.v = lo3(r.L.v); A.w = lo3(r.L.w);
   B.p = hi3(r.L.p); B.v = hi3(r.L.v); B.w = hi3(r.L.w);
@@ -477,14 +487,11 @@ __device__ __forceinline__ void contacts2(Rig2& r, const DevConst& C, V3 dA, V3 
       row_add(acc.cv, 1 + 2 * leg, c.dv); row_add(acc.ca, 1 + 2 * leg, c.dw);
     }
     if (WALLS && mB != 0u) {
-      const unsigned m = cull_candidates(B, C.s_foot * dB, C.r_leg, mB, C);
-      if (m != 0u) {
-        Imp c;
-        if (!wall_single(B, C.s_foot * dB, C.r_leg, C.inv_m_leg, m, C, c))
-          c = wall_group(B, C.s_foot * dB, C.r_leg, C.inv_m_leg, m, C);
-        B.v += c.dv; B.w += c.dw;
-        acc.Bv += c.dv; acc.Bw += c.dw;
-      }
+      Imp c;
+      if (!tip_wall(B, C.s_foot * dB, C.r_leg, C.inv_m_leg, mB, C, c))
+        c = wall_group(B, C.s_foot * dB, C.r_leg, C.inv_m_leg, mB, C);
+      B.v += c.dv; B.w += c.dw;
+      acc.Bv += c.dv; acc.Bw += c.dw;
     }
   }
   B.v += gv; B.w += gw;
@@ -493,15 +500,23 @@ __device__ __forceinline__ void contacts2(Rig2& r, const DevConst& C, V3 dA, V3 
 }
 
 template <bool WALLS>
-__device__ __forceinline__ void advance2(Rig2& r, const DevConst& C, unsigned& mT, unsigned& mA, unsigned& mB) {
+__device__ __forceinline__ void advance2(Rig2& r, const DevConst& C, unsigned& mT, unsigned& mA) {
   kinetic_t(r.T, C.h);
   kinetic2(r.L, C.h);
-  mT = mA = mB = 0u;
+  mT = mA = 0u;
   if (WALLS && C.n_walls > 0) {
     mT = wall_mask_at(C, 0, r.T.p.x, r.T.p.y);
     mA = wall_mask_at(C, 1, lo(r.L.p.x), lo(r.L.p.y));
-    mB = wall_mask_at(C, 2, hi(r.L.p.x), hi(r.L.p.y));
   }
+}
+
+// Candidate walls of the lower leg from its two capsule ends (tip_mask_at): issued as soon as the leg's rotated
+// direction dB is known, consumed by the contact section behind the joint math.
+template <bool WALLS>
+__device__ __forceinline__ unsigned lower_leg_wall_mask(const Body2& L, V3 dB, const DevConst& C) {
+  if (!WALLS || C.n_walls <= 0) return 0u;
+  const float px = hi(L.p.x), py = hi(L.p.y), ex = C.s_foot * dB.x, ey = C.s_foot * dB.y;
+  return tip_mask_at(C, px + ex, py + ey) | tip_mask_at(C, px - ex, py - ey);
 }
 
 // Loop-invariant packed constants of the lane.
@@ -522,7 +537,7 @@ __device__ __forceinline__ LegK2 leg_consts2(const DevConst& C, const LegK& k, f
 // All impulses carry the factor h (C.h_k = h*stiffness, ...), so `potential` is a plain add.
 template <bool WALLS>
 __device__ __forceinline__ void substep2(Rig2& r, const LegK& k, const LegK2& k2, const DevConst& C, int leg,
-                                         unsigned mT, unsigned mA, unsigned mB, ContactAcc& acc) {
+                                         unsigned mT, unsigned mA, ContactAcc& acc) {
   const Cols cT = rot_cols(r.T);
   const Cols2 cL = rot_cols2(r.L);
   // R u: every lever arm of the leg is a scalar times dT / dA / dB
@@ -531,6 +546,7 @@ __device__ __forceinline__ void substep2(Rig2& r, const LegK& k, const LegK2& k2
   const V3 xT = cross(r.T.w, dT);
   const V3x2 xL = cross(r.L.w, dL);
   const V3 dA = lo3(dL), xA = lo3(xL);
+  const unsigned mB = lower_leg_wall_mask<WALLS>(r.L, hi3(dL), C);
   // ---- joint anchors: child side packed (A at the hip, B at the ankle), parent side (T at the hip, A at the
   // ankle) scalar into fresh pairs. G = h*F on the child, (hip, ankle).
   const V3x2 cp = fma3(k2.sc, dL, r.L.p), cv = fma3(k2.sc, xL, r.L.v);

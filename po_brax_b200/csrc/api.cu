@@ -30,6 +30,8 @@ struct Handle {
   int device;
   cudaArray_t sdf_array = nullptr;       // wall candidate mask tables: layered 2D array behind a texture object
   cudaTextureObject_t sdf_tex = 0;
+  cudaArray_t tip_array = nullptr;       // lower-leg capsule-end candidate masks (finer cells), 2D array + texture object
+  cudaTextureObject_t tip_tex = 0;
   float4* walls = nullptr;
   float2* grid = nullptr;
 };
@@ -221,7 +223,7 @@ static std::vector<float2> gather_grid(const PobraxParams* p) {
 }
 
 static int build_dev_const(const PobraxParams* p, DevConst* Cp, std::vector<uint8_t>* sdf, std::vector<float2>* grid,
-                           std::vector<float4>* walls) {
+                           std::vector<float4>* walls, std::vector<uint8_t>* tip) {
   DevConst& C = *Cp;
   std::memset(&C, 0, sizeof(C));
   PobraxLayout L;
@@ -356,6 +358,46 @@ static int build_dev_const(const PobraxParams* p, DevConst* Cp, std::vector<uint
     C.sdf_bx = (float)(-x0 / cell); C.sdf_by = (float)(-y0 / cell);
     C.sdf_nx = nx; C.sdf_ny = ny;
   }
+  tip->clear();
+  if (C.n_walls > 0) {
+    // Capsule-END table of the lower leg (ant_physics.cuh tip_mask_at): bit w of a cell <=> some point of the cell is
+    // within r_leg of wall w's footprint, or within seg_foot + r_leg of one of the footprint's four vertices (the
+    // end lookups of a capsule then cover its interior points too, see tip_mask_at). 1/32 m cells; 1 mm of slack for
+    // float rounding and the texture unit's coordinate quantisation; border cells list every wall.
+    const double cell = 1.0 / 32.0, margin = 0.75, slack = 1e-3;
+    double x0 = 1e30, y0 = 1e30, x1 = -1e30, y1 = -1e30;
+    for (int w = 0; w < C.n_walls; ++w) {
+      x0 = std::fmin(x0, wlo[w][0]); y0 = std::fmin(y0, wlo[w][1]);
+      x1 = std::fmax(x1, whi[w][0]); y1 = std::fmax(y1, whi[w][1]);
+    }
+    x0 -= margin; y0 -= margin; x1 += margin; y1 += margin;
+    const int nx = (int)std::ceil((x1 - x0) / cell), ny = (int)std::ceil((y1 - y0) / cell);
+    if ((long long)nx * ny > (1 << 24)) return fail("wall extent unsupported (capsule-end table too large)");
+    const uint8_t all = (uint8_t)((1u << C.n_walls) - 1u);
+    tip->assign((size_t)nx * ny, all);
+    const double r_face = C.r_leg + slack, r_vert = C.seg_foot + C.r_leg + slack;
+    for (int iy = 1; iy < ny - 1; ++iy)
+      for (int ix = 1; ix < nx - 1; ++ix) {
+        const double cx0 = x0 + ix * cell - 1e-4, cx1 = x0 + (ix + 1) * cell + 1e-4;
+        const double cy0 = y0 + iy * cell - 1e-4, cy1 = y0 + (iy + 1) * cell + 1e-4;
+        uint8_t m = 0;
+        for (int w = 0; w < C.n_walls; ++w) {
+          const double dx = std::fmax(std::fmax(wlo[w][0] - cx1, 0.0), cx0 - whi[w][0]);
+          const double dy = std::fmax(std::fmax(wlo[w][1] - cy1, 0.0), cy0 - whi[w][1]);
+          bool near = std::sqrt(dx * dx + dy * dy) <= r_face;
+          for (int v = 0; v < 4 && !near; ++v) {
+            const double vx = (v & 1) ? whi[w][0] : wlo[w][0], vy = (v & 2) ? whi[w][1] : wlo[w][1];
+            const double ex = std::fmax(std::fmax(cx0 - vx, 0.0), vx - cx1), ey = std::fmax(std::fmax(cy0 - vy, 0.0), vy - cy1);
+            near = std::sqrt(ex * ex + ey * ey) <= r_vert;
+          }
+          if (near) m |= (uint8_t)(1u << w);
+        }
+        (*tip)[(size_t)iy * nx + ix] = m;
+      }
+    C.tip_inv_cell = (float)(1.0 / cell);
+    C.tip_bx = (float)(-x0 / cell); C.tip_by = (float)(-y0 / cell);
+    C.tip_nx = nx; C.tip_ny = ny;
+  }
   // ---- task
   C.dying_cost = p->dying_cost; C.visible_radius = p->visible_radius;
   for (int i = 0; i < 2; ++i) {
@@ -395,7 +437,8 @@ extern "C" int pobrax_create(const PobraxParams* p, int device, void** handle) {
   std::vector<uint8_t> sdf;
   std::vector<float2> grid;
   std::vector<float4> walls;
-  if (int rc = build_dev_const(p, &C, &sdf, &grid, &walls)) return rc;
+  std::vector<uint8_t> tip;
+  if (int rc = build_dev_const(p, &C, &sdf, &grid, &walls, &tip)) return rc;
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess) return fail_cuda("pobrax_create: no CUDA device (this library has no CPU path)", e);
@@ -441,6 +484,28 @@ extern "C" int pobrax_create(const PobraxParams* p, int device, void** handle) {
     }
     C.wall_tex = (unsigned long long)h->sdf_tex;
   }
+  if (!tip.empty()) {  // capsule-end table: plain 2D texture (point sampling, clamp, unnormalised coordinates)
+    cudaChannelFormatDesc fmt = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+    if ((e = cudaMallocArray(&h->tip_array, &fmt, (size_t)C.tip_nx, (size_t)C.tip_ny)) != cudaSuccess) {
+      cudaSetDevice(prev); pobrax_destroy(h); return fail_cuda("cudaMallocArray(capsule-end masks)", e);
+    }
+    if ((e = cudaMemcpy2DToArray(h->tip_array, 0, 0, tip.data(), (size_t)C.tip_nx, (size_t)C.tip_nx, (size_t)C.tip_ny,
+                                 cudaMemcpyHostToDevice)) != cudaSuccess) {
+      cudaSetDevice(prev); pobrax_destroy(h); return fail_cuda("cudaMemcpy2DToArray(capsule-end masks)", e);
+    }
+    cudaResourceDesc res = {};
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = h->tip_array;
+    cudaTextureDesc td = {};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    if ((e = cudaCreateTextureObject(&h->tip_tex, &res, &td, nullptr)) != cudaSuccess) {
+      cudaSetDevice(prev); pobrax_destroy(h); return fail_cuda("cudaCreateTextureObject(capsule-end masks)", e);
+    }
+    C.tip_tex = (unsigned long long)h->tip_tex;
+  }
   C.walls = h->walls;
   {  // per-device kernel attributes + occupancy for THIS handle's device (a process may hold handles on several GPUs)
     const char* what = "";
@@ -463,6 +528,8 @@ extern "C" int pobrax_destroy(void* handle) {
   cudaSetDevice(h->device);
   if (h->sdf_tex) cudaDestroyTextureObject(h->sdf_tex);
   if (h->sdf_array) cudaFreeArray(h->sdf_array);
+  if (h->tip_tex) cudaDestroyTextureObject(h->tip_tex);
+  if (h->tip_array) cudaFreeArray(h->tip_array);
   if (h->walls) cudaFree(h->walls);
   if (h->grid) cudaFree(h->grid);
   cudaSetDevice(prev);

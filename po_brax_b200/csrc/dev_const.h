@@ -58,6 +58,10 @@ struct DevConst {
                                              // unnormalised coordinates)
   float sdf_x0, sdf_y0, sdf_inv_cell, sdf_bx, sdf_by;   // sdf_bx = -x0 * inv_cell (cell = fma(p, inv_cell, b))
   int32_t sdf_nx, sdf_ny;
+  unsigned long long tip_tex;                // cudaTextureObject_t: [tip_ny][tip_nx] candidate-wall bit mask of a lower-leg
+                                             // capsule END at that xy cell (finer cells; ant_physics.cuh tip_mask_at)
+  float tip_inv_cell, tip_bx, tip_by;
+  int32_t tip_nx, tip_ny;
   // task
   float dying_cost, visible_radius;
   float hh_xy[2][2], priest_xy[2], hh_z, priest_z;

@@ -273,18 +273,19 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
   acc.ca = acc.cv + 3 * C.nb;
   {
     // Rotated substep loop, one code copy of each half (the kernel must fit the instruction cache):
-    // iteration s runs the dynamics of substep s-1 and then the kinetic update + wall-mask loads of substep s,
-    // so the three table loads are in flight during the next iteration's joint math.
+    // iteration s runs the dynamics of substep s-1 and then the kinetic update + torso / Aux wall-mask loads of
+    // substep s, so those table loads are in flight during the next iteration's joint math (the lower leg's two
+    // capsule-end lookups are issued inside substep2 as soon as its direction is known).
     // Inside the loop the Aux and the lower leg are the two halves of packed float32x2 registers (Rig2).
     constexpr bool W = KIND != POBRAX_ANT;
-    unsigned mT = 0u, mA = 0u, mB = 0u;
+    unsigned mT = 0u, mA = 0u;
     const int nsub = C.substeps;
     const LegK2 k2 = leg_consts2(C, k, act.x, act.y);
     Rig2 p = pack_rig(r);
 #pragma unroll 1
     for (int s = 0; s <= nsub; ++s) {
-      if (s > 0) substep2<W>(p, k, k2, C, leg, mT, mA, mB, acc);
-      if (s < nsub) advance2<W>(p, C, mT, mA, mB);
+      if (s > 0) substep2<W>(p, k, k2, C, leg, mT, mA, acc);
+      if (s < nsub) advance2<W>(p, C, mT, mA);
     }
     r = unpack_rig(p);
   }
@@ -651,7 +652,7 @@ reset_kernel(const __grid_constant__ DevConst C, const PobraxState S, const uint
     if (KIND != POBRAX_ANT && C.n_walls > 0) {
       mT = wall_mask_at(C, 0, r.T.p.x, r.T.p.y);
       mA = wall_mask_at(C, 1, r.A.p.x, r.A.p.y);
-      mB = wall_mask_at(C, 2, r.B.p.x, r.B.p.y);
+      mB = lower_leg_wall_mask<true>(tmp.L, dB, C);
     }
     contacts2<KIND != POBRAX_ANT>(tmp, C, dA, dB, mT, mA, mB, leg, ct);
   }

@@ -76,7 +76,7 @@ using namespace pobrax;
 
 struct EmuHandle {
   DevConst C;
-  std::vector<uint8_t> sdf;
+  std::vector<uint8_t> sdf, tip;
   std::vector<float2> grid;
   std::vector<float4> walls;
 };
@@ -96,7 +96,7 @@ void body_to(const Body& o, float* pos, float* rot, float* vel, float* ang, int 
   ang[3 * b] = o.w.x; ang[3 * b + 1] = o.w.y; ang[3 * b + 2] = o.w.z;
 }
 
-struct LaneState { Rig2 p; V3 Bv, Bw; unsigned mT, mA, mB; };
+struct LaneState { Rig2 p; V3 Bv, Bw; unsigned mT, mA; };
 
 // One env step of one env, the way step_kernel runs it (kernels.cu, the rotated substep loop), WALLS as a template.
 template <bool W>
@@ -114,7 +114,7 @@ int step_env(const DevConst& C, float* pos, float* rot, float* vel, float* ang, 
     k2[l] = leg_consts2(C, k[l], act[2 * l], act[2 * l + 1]);
     L[l].p = pack_rig(r);
     L[l].Bv = L[l].Bw = mk(0.f, 0.f, 0.f);
-    L[l].mT = L[l].mA = L[l].mB = 0u;
+    L[l].mT = L[l].mA = 0u;
   }
   std::vector<float> row_cv(3 * nb, 0.f), row_ca(3 * nb, 0.f);   // the staged observation row's contact blocks
   emu::Quad& q = emu::q;
@@ -136,7 +136,7 @@ int step_env(const DevConst& C, float* pos, float* rot, float* vel, float* ang, 
           ContactAcc acc;
           acc.Bv = L[l].Bv; acc.Bw = L[l].Bw;
           acc.cv = row_cv.data(); acc.ca = row_ca.data();
-          substep2<W>(L[l].p, k[l], k2[l], C, l, L[l].mT, L[l].mA, L[l].mB, acc);
+          substep2<W>(L[l].p, k[l], k2[l], C, l, L[l].mT, L[l].mA, acc);
           L[l].Bv = acc.Bv; L[l].Bw = acc.Bw;
           if (q.call > emu::kMaxCalls) return 3;
           calls = q.call;
@@ -147,7 +147,7 @@ int step_env(const DevConst& C, float* pos, float* rot, float* vel, float* ang, 
       }
     }
     if (s < C.substeps)
-      for (int l = 0; l < 4; ++l) advance2<W>(L[l].p, C, L[l].mT, L[l].mA, L[l].mB);
+      for (int l = 0; l < 4; ++l) advance2<W>(L[l].p, C, L[l].mT, L[l].mA);
   }
   for (int l = 0; l < 4; ++l) {
     const Rig r = unpack_rig(L[l].p);
@@ -170,9 +170,10 @@ extern "C" {
 // (pobrax_last_error() of THIS library has the message).
 int emu_create(const PobraxParams* p, void** handle) {
   EmuHandle* h = new EmuHandle();
-  if (int rc = build_dev_const(p, &h->C, &h->sdf, &h->grid, &h->walls)) { delete h; return rc; }
+  if (int rc = build_dev_const(p, &h->C, &h->sdf, &h->grid, &h->walls, &h->tip)) { delete h; return rc; }
   h->C.walls = h->walls.data();
   h->C.wall_tex = (unsigned long long)(uintptr_t)h->sdf.data();
+  h->C.tip_tex = (unsigned long long)(uintptr_t)h->tip.data();
   *handle = h;
   return 0;
 }

@@ -32,4 +32,10 @@ inline unsigned wall_mask_at(const DevConst& C, int kind, float x, float y) {
   return reinterpret_cast<const unsigned char*>(C.wall_tex)[((size_t)kind * C.sdf_ny + iy) * C.sdf_nx + ix];
 }
 
+inline unsigned tip_mask_at(const DevConst& C, float x, float y) {
+  const int ix = (int)fminf(fmaxf(floorf(fmaf(x, C.tip_inv_cell, C.tip_bx)), 0.0f), (float)(C.tip_nx - 1));
+  const int iy = (int)fminf(fmaxf(floorf(fmaf(y, C.tip_inv_cell, C.tip_by)), 0.0f), (float)(C.tip_ny - 1));
+  return reinterpret_cast<const unsigned char*>(C.tip_tex)[(size_t)iy * C.tip_nx + ix];
+}
+
 }  // namespace pobrax

@@ -112,6 +112,27 @@ __device__ __forceinline__ void foot_ground(const Body& b, V3 e, float r, float 
   dw = mk(ry * Jn - rz * jy, rz * jx - rx * Jn, rx * jy - ry * jx);
 }
 
+// The torso's capsule_plane candidate: a sphere of radius r centred on the body (rel = (0, 0, -r)) on the ground plane
+// -- `impulse` for n = e_z with the lever's zero terms dropped (rel x n = 0: no angular term in the effective mass, the
+// normal impulse carries no torque). Inline: an ant lying on its back keeps this contact live for the rest of its
+// episode, in every substep.
+__device__ __forceinline__ void torso_ground(const Body& b, float r, float inv_m, const DevConst& C, V3& dv, V3& dw) {
+  dv = dw = mk(0.f, 0.f, 0.f);
+  const float pen = r - b.p.z;
+  const float vx = fmaf(-r, b.w.y, b.v.x), vy = fmaf(r, b.w.x, b.v.y), nv = b.v.z;   // v + w x rel
+  const float rden = rcp_ftz(inv_m);
+  const float J = (C.baumgarte * pen - (1.0f + C.elasticity) * nv) * rden;
+  if (!((pen > 0.0f) && (nv < 0.0f) && (J > 0.0f))) return;
+  dv.z = inv_m * J;
+  const float nd = sqrt_pos(fmaf(vx, vx, vy * vy));
+  if (nd > 0.01f) {
+    const float cd = -fminf(nd * rden, C.friction * J) * rcp_ftz(1e-6f + nd);
+    const float jx = cd * vx, jy = cd * vy;
+    dv.x = inv_m * jx; dv.y = inv_m * jy;
+    dw = mk(r * jy, -r * jx, 0.f);          // rel x (jx, jy, 0)
+  }
+}
+
 __device__ __forceinline__ V3 clamp3(V3 p, V3 lo, V3 hi) {
   return mk(fminf(fmaxf(p.x, lo.x), hi.x), fminf(fmaxf(p.y, lo.y), hi.y), fminf(fmaxf(p.z, lo.z), hi.z));
 }
@@ -138,16 +159,10 @@ __device__ __forceinline__ float seg_box_t(V3 a, V3 d, V3 lo, V3 hi) {
   return den > 0.0f ? tl - gl * (tr - tl) / den : tl;
 }
 
-// The rare contacts, out of line so the substep loop stays small (I-cache) and lean (registers):
-//  plane = 0: capsule (segment p + e .. p - e, radius rad) vs the axis-aligned Arena box [lo, hi]: one contact at
-//             the closest box point, normal (seg_pt - box_pt)/(1e-6 + d), penetration rad - d;
-//  plane = 1: sphere (e = 0) vs the ground plane z = 0 (the torso's capsule_plane candidate).
-__device__ __forceinline__ Imp contact_general(V3 p, V3 e, V3 v, V3 w, float rad, float inv_m, V3 lo, V3 hi, int plane,
+// A rare contact (evaluated out of line, see rare_group): capsule (segment p + e .. p - e, radius rad) vs the axis-aligned
+// Arena box [lo, hi]: one contact at the closest box point, normal (seg_pt - box_pt)/(1e-6 + d), penetration rad - d.
+__device__ __forceinline__ Imp contact_general(V3 p, V3 e, V3 v, V3 w, float rad, float inv_m, V3 lo, V3 hi,
                                                float baumgarte, float friction, float elasticity) {
-  if (plane) {
-    const V3 rel = mk(0.f, 0.f, -rad);
-    return impulse(rel, v + cross(w, rel), mk(0.f, 0.f, 1.f), rad - p.z, inv_m, baumgarte, friction, elasticity);
-  }
   const V3 a = p + e;
   const V3 d = (p - e) - a;
   const float t = seg_box_t(a, d, lo, hi);
@@ -233,18 +248,14 @@ __device__ __forceinline__ void quad_sum2(V3& a, V3& b) {
   a = mk(lo(p0), hi(p0), lo(p1)); b = mk(hi(p1), lo(p2), hi(p2));
 }
 
-// The rare collider groups of one body, out of line (one copy, register-passed arguments) so the substep loop
-// stays small enough for the instruction cache:
-//  m != 0: the Arena group -- capsule (segment p + e .. p - e, radius rad) vs its candidate boxes (bit mask m,
-//          boxes in global memory). Contacts are summed and divided by (1e-8 + #contacts with a non-zero dv).
-//          A box separated from the segment's bounding box by >= rad along some axis cannot touch: skipped
-//          exactly.
-//  m == 0: the torso's ground-plane candidate (sphere vs z = 0).
+// The Arena collider group of one body, out of line (one copy, register-passed arguments) so the substep loop
+// stays small enough for the instruction cache: capsule (segment p + e .. p - e, radius rad) vs its candidate boxes
+// (bit mask m != 0, boxes in global memory). Contacts are summed and divided by (1e-8 + #contacts with a non-zero dv).
+// A box separated from the segment's bounding box by >= rad along some axis cannot touch: skipped exactly.
 __device__ __noinline__ Imp rare_group(V3 p, V3 e, V3 v, V3 w, float rad, float inv_m, unsigned m,
                                        const float4* __restrict__ walls, float baumgarte, float friction,
                                        float elasticity) {
   const V3 zero = mk(0.f, 0.f, 0.f);
-  if (m == 0u) return contact_general(p, zero, v, w, rad, inv_m, zero, zero, 1, baumgarte, friction, elasticity);
   Imp o;
   o.dv = o.dw = zero;
   o.hit = 0.0f;
@@ -260,7 +271,7 @@ __device__ __noinline__ Imp rare_group(V3 p, V3 e, V3 v, V3 w, float rad, float 
     const float gap = fmaxf(fmaxf(fmaxf(lo.x - smax.x, smin.x - hi.x), fmaxf(lo.y - smax.y, smin.y - hi.y)),
                             fmaxf(lo.z - smax.z, smin.z - hi.z));
     if (gap < rad) {
-      const Imp c = contact_general(p, e, v, w, rad, inv_m, lo, hi, 0, baumgarte, friction, elasticity);
+      const Imp c = contact_general(p, e, v, w, rad, inv_m, lo, hi, baumgarte, friction, elasticity);
       o.dv += c.dv; o.dw += c.dw; o.hit += c.hit;
     }
   } while (m);
@@ -469,9 +480,7 @@ __device__ __forceinline__ void contacts2(Rig2& r, const DevConst& C, V3 dA, V3 
     if (hitT || mT != 0u) {
       Imp t;
       t.dv = t.dw = zero;
-      if (hitT)
-        t = rare_group(r.T.p, zero, r.T.v, r.T.w, C.r_torso, C.inv_m_torso, 0u, C.walls, C.baumgarte, C.friction,
-                       C.elasticity);
+      if (hitT) torso_ground(r.T, C.r_torso, C.inv_m_torso, C, t.dv, t.dw);
       if (WALLS && mT != 0u && !wall_far_single(r.T, zero, C.r_torso, mT, C)) {
         // torso and Aux in wall contact are rare (the lower legs reach furthest): no inline narrow phase, one code
         // copy out of line behind the inline out-of-reach guard

@@ -109,7 +109,9 @@ class System:
     """brax.System for Ant-family configs (1-DoF revolute joints, torque actuators, capsule/sphere
     bodies vs one plane and vs axis-aligned boxes of a frozen Arena body)."""
 
-    def __init__(self, cfg: dict, dtype=np.float32, walls: bool = True):
+    def __init__(self, cfg: dict, dtype=np.float32, walls=True):
+        """walls: True = the documented box substitute (what the CUDA path implements), False = no Arena colliders,
+        'mesh' = brax's capsule-vs-triangulated-box collider as recalled (ANALYSIS ONLY, see _wall_contacts_mesh)."""
         self.cfg = cfg
         self.dtype = dt = dtype
         self.names = [b['name'] for b in cfg['bodies']]
@@ -206,6 +208,9 @@ class System:
                 if bi == self.arena:
                     boxes.append(np.concatenate([cpos - hs, cpos + hs]))
         self.boxes = np.array(boxes, dt).reshape(-1, 6) if walls else np.zeros((0, 6), dt)
+        self.wall_mode = 'mesh' if walls == 'mesh' else 'box'
+        if self.wall_mode == 'mesh':
+            self._build_mesh(cfg)
         self.defaults = cfg.get('defaults', [])
         self.track_margin = False   # test aid, see _note_margin
         self.margin = None
@@ -488,9 +493,138 @@ class System:
         dvel, dang = self._impulse(pos, b, box_p, cvel, n, pen, degenerate=(dist == 0), surface=surface)
         return self._group_reduce(N, b, dvel, dang)
 
+    # ------------------------------------------------------------------ brax's mesh wall collider (analysis only)
+    # brax 0.0.12 resolves ('capsule', 'box') pairs through capsule_mesh against a TriangulatedBox. RECALLED from the
+    # published source (brax/physics/{geometry,colliders,geometry_utils? math}.py), not pinned by any reference artefact:
+    #   corners  = itertools.product((-1, 1), repeat=3) * halfsize       (corner i: x = bit 2, y = bit 1, z = bit 0)
+    #   faces    = [0,4,1, 4,5,1 | 0,2,4, 2,6,4 | 6,5,4, 6,7,5 | 2,3,6, 3,7,6 | 1,5,3, 5,7,3 | 0,1,2, 1,3,2]
+    #              (-y, -z, +x, +y, +z, -x; two triangles per side), rotated by the collider's euler rotation
+    #   per (capsule, triangle): closest_segment_triangle_points -> contact at the TRIANGLE point, normal
+    #   (seg_pt - tri_pt) / (1e-6 + dist), penetration radius - dist; all triangle contacts of all boxes for one
+    #   body form one group: summed and divided by the number of active ones.
+    # Used by oracle/wall_deviation.py and tests/test_wall_collider.py to quantify how the box substitute differs.
+    _BOX_FACES = np.array([0, 4, 1, 4, 5, 1, 0, 2, 4, 2, 6, 4, 6, 5, 4, 6, 7, 5, 2, 3, 6, 3, 7, 6, 1, 5, 3, 5, 7, 3,
+                           0, 1, 2, 1, 3, 2]).reshape(12, 3)
+    _BOX_NORMALS = np.repeat(np.array([[0, -1., 0], [0, 0, -1.], [1., 0, 0], [0, 1., 0], [0, 0, 1.], [-1., 0, 0]]), 2, axis=0)
+
+    def _build_mesh(self, cfg):
+        dt = self.dtype
+        corners = np.array([[x, y, z] for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)], np.float64)
+        tris, normals = [], []
+        for b in cfg['bodies']:
+            if b['name'] != 'Arena':
+                continue
+            for c in b.get('colliders', []):
+                if 'box' not in c:
+                    continue
+                hs = np.array(_vec(c['box']['halfsize']), np.float64)
+                q = euler_to_quat(_vec(c.get('rotation')), np.float64)
+                v = rotate(corners * hs, np.broadcast_to(q, (8, 4))) + np.array(_vec(c.get('position')), np.float64)
+                tris.append(v[self._BOX_FACES])                                           # [12, 3, 3]
+                normals.append(rotate(self._BOX_NORMALS, np.broadcast_to(q, (12, 4))))
+        self.mesh_tris = np.array(tris, dt)          # [nbox, 12, 3 vertices, 3] in the Arena body frame
+        self.mesh_normals = np.array(normals, dt)    # [nbox, 12, 3]
+
+    @staticmethod
+    def _closest_segment_point(a, b, pt):
+        ab = b - a
+        t = dot(pt - a, ab) / (dot(ab, ab) + 1e-6)
+        return a + np.clip(t, 0, 1)[..., None] * ab
+
+    def _closest_segment_segment(self, a0, a1, b0, b1):
+        """brax geometry.closest_segment_to_segment_points."""
+        def normalize(v):
+            n = safe_norm(v)
+            return v / (1e-6 + n)[..., None], n
+        dir_a, len_a = normalize(a1 - a0)
+        dir_b, len_b = normalize(b1 - b0)
+        ha, hb = len_a * 0.5, len_b * 0.5
+        a_mid, b_mid = a0 + dir_a * ha[..., None], b0 + dir_b * hb[..., None]
+        trans = a_mid - b_mid
+        dd, dat, dbt = dot(dir_a, dir_b), dot(dir_a, trans), dot(dir_b, trans)
+        denom = 1 - dd * dd
+        ta = (-dat + dd * dbt) / (denom + 1e-6)
+        tb = dbt + ta * dd
+        ta, tb = np.clip(ta, -ha, ha), np.clip(tb, -hb, hb)
+        best_a, best_b = a_mid + dir_a * ta[..., None], b_mid + dir_b * tb[..., None]
+        new_a = self._closest_segment_point(a0, a1, best_b)
+        new_b = self._closest_segment_point(b0, b1, best_a)
+        d1, d2 = dot(new_a - best_b, new_a - best_b), dot(new_b - best_a, new_b - best_a)
+        pick = (d1 < d2)[..., None]
+        return np.where(pick, new_a, best_a), np.where(pick, best_b, new_b)
+
+    def _closest_segment_triangle(self, a, b, p0, p1, p2, n):
+        """brax geometry.closest_segment_triangle_points: min over the three edge pairs and the plane candidate (the
+        segment point nearest the plane, if its projection falls inside the triangle); ties averaged."""
+        cands = [self._closest_segment_segment(a, b, p0, p1), self._closest_segment_segment(a, b, p1, p2),
+                 self._closest_segment_segment(a, b, p0, p2)]
+        d = dot(p0, n)
+        den = dot(n, b - a)
+        t = (d - dot(n, a)) / (den + 1e-6 * (den == 0))
+        seg4 = a + np.clip(t, 0, 1)[..., None] * (b - a)
+        tri4 = seg4 - (dot(seg4, n) - d)[..., None] * n
+        # inside test: same side of all three edges
+        def side(u, v):
+            return dot(cross(v - u, tri4 - u), n)
+        s0, s1, s2 = side(p0, p1), side(p1, p2), side(p2, p0)
+        inside = ((s0 >= 0) & (s1 >= 0) & (s2 >= 0)) | ((s0 <= 0) & (s1 <= 0) & (s2 <= 0))
+        dist = [dot(sp - tp, sp - tp) for sp, tp in cands]
+        dist.append(np.where(inside, dot(seg4 - tri4, seg4 - tri4), np.inf))
+        cands.append((seg4, tri4))
+        dist = np.stack(dist, axis=-1)
+        mask = (dist == dist.min(axis=-1, keepdims=True)).astype(a.dtype)
+        seg = sum(c[0] * mask[..., i:i + 1] for i, c in enumerate(cands)) / mask.sum(-1, keepdims=True)
+        tri = sum(c[1] * mask[..., i:i + 1] for i, c in enumerate(cands)) / mask.sum(-1, keepdims=True)
+        return seg, tri
+
+    def _wall_contacts_mesh(self, qp: QP):
+        """capsule_mesh over every (ant capsule, Arena box) pair whose bounding boxes come within the capsule radius
+        (exact cull: further apart, all 12 triangle contacts have penetration < 0 and contribute exactly zero)."""
+        N, nb = qp.pos.shape[0], self.num_bodies
+        zv, za = np.zeros((N, nb, 3), self.dtype), np.zeros((N, nb, 3), self.dtype)
+        if len(self.boxes) == 0 or len(self.cap_body) == 0:
+            return zv, za
+        apos = qp.pos[:, self.arena]                                           # [N,3]
+        cb = self.cap_body
+        pos, rot = qp.pos[:, cb], qp.rot[:, cb]
+        a_w = pos + rotate(np.broadcast_to(self.cap_a, pos.shape), rot)        # [N,K,3]
+        b_w = pos + rotate(np.broadcast_to(self.cap_b, pos.shape), rot)
+        smin, smax = np.minimum(a_w, b_w), np.maximum(a_w, b_w)
+        lo = apos[:, None, None, :] + self.boxes[None, None, :, :3]            # [N,1,X,3]
+        hi = apos[:, None, None, :] + self.boxes[None, None, :, 3:]
+        gap = np.maximum(lo - smax[:, :, None, :], smin[:, :, None, :] - hi).max(-1)   # [N,K,X]
+        e, k, x = np.nonzero(gap < (self.cap_rad[None, :, None] + 1e-3))
+        if len(e) == 0:
+            return zv, za
+        body = cb[k]
+        a, b = a_w[e, k][:, None, :], b_w[e, k][:, None, :]                    # [M,1,3]
+        tri = apos[e][:, None, None, :] + self.mesh_tris[x]                    # [M,12,3,3]
+        n = self.mesh_normals[x]                                               # [M,12,3] (Arena rot = identity)
+        sp, tp = self._closest_segment_triangle(np.broadcast_to(a, tri[:, :, 0].shape), np.broadcast_to(b, tri[:, :, 0].shape),
+                                                tri[:, :, 0], tri[:, :, 1], tri[:, :, 2], n)
+        dvec = sp - tp
+        dist = safe_norm(dvec)
+        normal = dvec / (self.dtype(1e-6) + dist)[..., None]
+        pen = self.cap_rad[k][:, None] - dist
+        bp, bv, bw = qp.pos[e, body][:, None, :], qp.vel[e, body][:, None, :], qp.ang[e, body][:, None, :]
+        cvel = bv + cross(np.broadcast_to(bw, tp.shape), tp - bp)
+        keep, self.track_margin = self.track_margin, False
+        dvel, dang = self._impulse(bp, body[:, None], tp, cvel, normal, pen)
+        self.track_margin = keep
+        hit = np.any(dvel != 0, axis=-1).astype(self.dtype)                    # [M,12]
+        cnt = np.zeros((N, nb), self.dtype)
+        np.add.at(cnt, (e, body), hit.sum(-1))
+        np.add.at(zv, (e, body), dvel.sum(1))
+        np.add.at(za, (e, body), dang.sum(1))
+        d = (self.dtype(1e-8) + cnt)[..., None]
+        self.last_mesh_active = cnt
+        prev = getattr(self, 'mesh_active_max', None)   # analysis aid: callers reset it to None before a step
+        self.mesh_active_max = cnt if prev is None else np.maximum(prev, cnt)
+        return (zv / d).astype(self.dtype), (za / d).astype(self.dtype)
+
     def _contacts(self, qp: QP):
         gv, ga = self._ground_contacts(qp)
-        wv, wa = self._wall_contacts(qp)
+        wv, wa = self._wall_contacts_mesh(qp) if self.wall_mode == 'mesh' else self._wall_contacts(qp)
         return gv + wv, ga + wa
 
     # ------------------------------------------------------------------ step / info

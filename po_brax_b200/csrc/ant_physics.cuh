@@ -184,7 +184,8 @@ __device__ __forceinline__ Imp contact_general(V3 p, V3 e, V3 v, V3 w, float rad
 
 // Candidate walls of a body centred at (x, y): bit w of the byte set <=> wall w is within that body type's
 // reach of the table cell (exact rectangle-rectangle distance in xy, so culling stays exact). One table per
-// body type `kind` (0 torso sphere, 1 Aux capsule, 2 lower-leg capsule), read through a layered 2D texture:
+// body type `kind` (0 torso sphere, 1 Aux capsule; the lower leg has its capsule-end table below), read through a
+// layered 2D texture:
 // cell = floor((p - origin) / cell_size) is one FMA per axis here, and the texture unit does the float -> cell
 // conversion, the clamp onto the border cells (which list every wall, as does everything outside the table) and the
 // addressing -- 3 instructions per lookup instead of 10 (30 lookups per lane and step).

@@ -339,9 +339,9 @@ static int build_dev_const(const PobraxParams* p, DevConst* Cp, std::vector<uint
     // everything outside the table, which clamps onto them) list every wall.
     const uint8_t all = (uint8_t)((1u << C.n_walls) - 1u);
     const size_t plane = (size_t)nx * ny;
-    sdf->assign(3 * plane, all);
-    const double reach[3] = {C.r_torso + 2e-3, C.seg_aux + C.r_leg + 2e-3, C.seg_foot + C.r_leg + 2e-3};
-    for (int k = 0; k < 3; ++k)
+    sdf->assign(2 * plane, all);
+    const double reach[2] = {C.r_torso + 2e-3, C.seg_aux + C.r_leg + 2e-3};   // (the lower leg has its own table below)
+    for (int k = 0; k < 2; ++k)
       for (int iy = 1; iy < ny - 1; ++iy)
         for (int ix = 1; ix < nx - 1; ++ix) {
           const double cx0 = x0 + ix * cell - 1e-4, cx1 = x0 + (ix + 1) * cell + 1e-4;
@@ -459,9 +459,9 @@ extern "C" int pobrax_create(const PobraxParams* p, int device, void** handle) {
     if ((e = cudaMalloc(&h->walls, walls.size() * sizeof(float4))) != cudaSuccess) { cudaFree(h->grid); delete h; cudaSetDevice(prev); return fail_cuda("cudaMalloc(walls)", e); }
     cudaMemcpy(h->walls, walls.data(), walls.size() * sizeof(float4), cudaMemcpyHostToDevice);
   }
-  if (!sdf.empty()) {  // layered 2D texture over the three tables (point sampling, clamp, unnormalised coordinates)
+  if (!sdf.empty()) {  // layered 2D texture over the two body-centre tables (torso, Aux) (point sampling, clamp, unnormalised coordinates)
     cudaChannelFormatDesc fmt = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
-    cudaExtent ext = make_cudaExtent((size_t)C.sdf_nx, (size_t)C.sdf_ny, 3);
+    cudaExtent ext = make_cudaExtent((size_t)C.sdf_nx, (size_t)C.sdf_ny, 2);
     if ((e = cudaMalloc3DArray(&h->sdf_array, &fmt, ext, cudaArrayLayered)) != cudaSuccess) {
       cudaSetDevice(prev); pobrax_destroy(h); return fail_cuda("cudaMalloc3DArray(wall masks)", e);
     }

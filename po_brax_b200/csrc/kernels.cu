@@ -263,9 +263,9 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
   Key tag_knext; tag_knext.k0 = tag_knext.k1 = 0u;
   if (KIND == POBRAX_ANT_TAG) {
     Key key; key.k0 = S.rng[2 * e]; key.k1 = S.rng[2 * e + 1];
-    Key k1;
-    split2(key, tag_knext, k1);
-    tag_choice = randint4(k1);
+    Key k1;   // the 4 lanes of an env hold the same key: each pair of lanes shares the two blocks of a split
+    split2_pair(key, lane, tag_knext, k1);
+    tag_choice = randint4_pair(k1, lane);
   }
   ContactAcc acc;
   acc.Bv = acc.Bw = mk(0.f, 0.f, 0.f);

@@ -61,6 +61,28 @@ __host__ __device__ __forceinline__ void split2(Key key, Key& a, Key& b) {
   a.k0 = x0; a.k1 = y0; b.k0 = x1; b.k1 = y1;
 }
 
+#ifdef __CUDACC__
+// split(key, 2) computed by a PAIR of lanes that hold the same key (lane parity picks the block: even lanes the
+// counters (0, 2), odd lanes (1, 3)); the halves are exchanged with two xor-shuffles. Same bits as split2, one
+// threefry block per lane instead of two. All 32 lanes must call it.
+__device__ __forceinline__ void split2_pair(Key key, int lane, Key& a, Key& b) {
+  const uint32_t odd = (uint32_t)(lane & 1);
+  uint32_t x0 = odd, x1 = 2u + odd;
+  threefry2x32(key, x0, x1);
+  const uint32_t p0 = __shfl_xor_sync(0xffffffffu, x0, 1), p1 = __shfl_xor_sync(0xffffffffu, x1, 1);
+  a.k0 = odd ? p0 : x0; a.k1 = odd ? x0 : p0;
+  b.k0 = odd ? p1 : x1; b.k1 = odd ? x1 : p1;
+}
+// randint4 with its split shared by a lane pair
+__device__ __forceinline__ int randint4_pair(Key key, int lane) {
+  Key a, b;
+  split2_pair(key, lane, a, b);
+  uint32_t x0 = 0, x1 = 0;
+  threefry2x32(b, x0, x1);
+  return (int)(x0 & 3u);
+}
+#endif
+
 // uniform bits -> float in [0,1): bitcast((bits >> 9) | 0x3F800000) - 1
 __host__ __device__ __forceinline__ float bits_to_unit(uint32_t bits) {
   union { uint32_t u; float f; } c;

@@ -34,6 +34,8 @@ def load():
         _lib.emu_create.restype = C.c_int
         _lib.emu_step.restype = C.c_int
         _lib.emu_num_bodies.restype = C.c_int
+        _lib.emu_tip_masks.restype = C.c_int
+        _lib.emu_walls.restype = C.c_int
         _lib.emu_destroy.restype = None
         _lib.pobrax_last_error.restype = C.c_char_p
     return _lib

@@ -182,6 +182,24 @@ void emu_destroy(void* handle) { delete static_cast<EmuHandle*>(handle); }
 
 int emu_num_bodies(void* handle) { return static_cast<EmuHandle*>(handle)->C.nb; }
 
+// The lower leg's capsule-end table (ant_physics.cuh tip_mask_at) at n points, and the handle's wall boxes, for the
+// exact-cull property test (tests/test_host_emu.py).
+int emu_tip_masks(void* handle, long n, const float* xy, unsigned* out) {
+  const DevConst& C = static_cast<EmuHandle*>(handle)->C;
+  if (C.n_walls <= 0) return 1;
+  for (long i = 0; i < n; ++i) out[i] = tip_mask_at(C, xy[2 * i], xy[2 * i + 1]);
+  return 0;
+}
+int emu_walls(void* handle, float* lo_hi /* [n_walls][6] */) {
+  const EmuHandle* h = static_cast<EmuHandle*>(handle);
+  for (int w = 0; w < h->C.n_walls; ++w) {
+    const float4 l = h->walls[2 * w], u = h->walls[2 * w + 1];
+    const float v[6] = {l.x, l.y, l.z, u.x, u.y, u.z};
+    for (int c = 0; c < 6; ++c) lo_hi[6 * w + c] = v[c];
+  }
+  return h->C.n_walls;
+}
+
 // brax.System.step on n envs, in place: QP arrays [n][nb][3|4] (brax body order; only the 9 ant bodies move),
 // act [n][8], cv / ca [n][nb][3] = Info.contact.vel / .ang summed over the substeps (unclipped).
 int emu_step(void* handle, long n, float* pos, float* rot, float* vel, float* ang, const float* act, float* cv,

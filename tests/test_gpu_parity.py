@@ -75,9 +75,10 @@ def test_reset_parity(kind):
     assert (P.t2n(got.info['steps']) == 0).all()
 
 
-def _ambiguous_contacts(oenv, qp, eps=1e-5):
+def _ambiguous_contacts(oenv, qp, eps=1e-5, walls_only=False):
     """[N, 9] bool: bodies with a ground-contact candidate whose |penetration| < eps (sign decided by rounding),
-    or (walls) a capsule within eps of touching a wall."""
+    or (walls) a capsule within eps of touching a wall. walls_only + eps=inf: bodies whose capsule is within its
+    radius of a wall box (touching)."""
     from oracle import brax_v1 as bx
     s = oenv.sys
     n = qp.pos.shape[0]
@@ -85,8 +86,9 @@ def _ambiguous_contacts(oenv, qp, eps=1e-5):
     b = s.cp_body
     end_w = qp.pos[:, b] + bx.rotate(np.broadcast_to(s.cp_end, qp.pos[:, b].shape), qp.rot[:, b])
     pen = -(end_w[..., 2] - s.cp_rad)
-    for k, body in enumerate(b):
-        amb[:, body] |= np.abs(pen[:, k]) < eps
+    if not walls_only:
+        for k, body in enumerate(b):
+            amb[:, body] |= np.abs(pen[:, k]) < eps
     if len(s.boxes):
         nbx = len(s.boxes)
         bb = np.repeat(s.cap_body, nbx)
@@ -99,7 +101,7 @@ def _ambiguous_contacts(oenv, qp, eps=1e-5):
         b_w = pos + bx.rotate(np.broadcast_to(cb, pos.shape), rot)
         sp, bp = s._closest_segment_box(a_w, b_w, apos + box[:, :3], apos + box[:, 3:])
         d = np.sqrt(((sp - bp) ** 2).sum(-1))
-        near = np.abs(rad - d) < eps
+        near = (np.abs(rad - d) < eps) if np.isfinite(eps) else ((d < rad) & (d > 0))
         for k, body in enumerate(bb):
             amb[:, body] |= near[:, k]
     return amb
@@ -136,7 +138,18 @@ def test_step_teacher_forced_at_baseline_sizes(kind, n, T):
     print(f'\n[parity] {kind} n={n} T={T}: {st}')
 
 
-def _teacher_forced(kind, n, T, init_box=None, c_step=False):
+@pytest.mark.parametrize('kind,n', [('ant_heavenhell', 32768), ('ant_tag', 32768)])
+def test_step_teacher_forced_ants_piled_up_along_the_walls(kind, n):
+    """The wall paths at scale: the oracle first walks the batch 250 steps under a PERIODIC action sequence (a gait:
+    the ants travel metres and pile up along the walls -- 15-20 % of the envs touch one in any step, against 0-12 %
+    from a reset), then every env is teacher-forced as usual. Exercises the capsule-end tables, `tip_wall`, the
+    out-of-line group and fallen ants (torso on the ground) on tens of thousands of envs."""
+    st = _teacher_forced(kind, n, 3, c_step=True, preroll=(250, 4))
+    print(f'\n[parity] {kind} n={n} after a 250-step gait: {st}')
+    assert st['wall_contact_envs'] > 0.05 * n, st
+
+
+def _teacher_forced(kind, n, T, init_box=None, c_step=False, preroll=None):
     """One env step from identical states, T times along an oracle rollout. Every env must meet the TIGHT gates of
     tests/_parity.py against the oracle's step -- or, where the oracle reports a rounding-ambiguous contact / actuator
     decision in that step, against the oracle's step with some of those decisions taken the other way (two-branch
@@ -153,11 +166,18 @@ def _teacher_forced(kind, n, T, init_box=None, c_step=False):
         oenv._init_lo, oenv._init_hi = np.array(init_box[0], np.float32), np.array(init_box[1], np.float32)
         kw['init_ant_pos'] = init_box
     s = oenv.reset(keys)
+    if preroll is not None:   # physics-only walk under a periodic action sequence (the task state stays as reset)
+        steps, period = preroll
+        gait = np.random.default_rng(3).uniform(-1, 1, (period, n, 8)).astype(np.float32)
+        qp = s.qp
+        for t in range(steps):
+            qp, _ = oenv.sys.step(qp, gait[t % period])
+        s = s.replace(qp=qp)
     env = _make(kind, n, auto_reset=False, episode_length=1000, **kw)
     rng = tf.prng_key(1)
     oenv.sys.track_margin = True
     stats = {'aux_wall_contacts': 0, 'torso_contacts': 0, 'marginal': 0.0, 'other_branch': 0, 'unexplained': 0,
-             'worst_unexplained_share': 0.0}
+             'worst_unexplained_share': 0.0, 'wall_contact_envs': 0}
     Pc = 1 if kind == 'ant' else 3
     for t in range(T):
         rng, a = P.actions_for(rng, n)
@@ -185,6 +205,8 @@ def _teacher_forced(kind, n, T, init_box=None, c_step=False):
         cvel = nxt.obs[:, Pc + 26:Pc + 26 + 3 * nb].reshape(n, nb, 3)   # clip(contact.vel): Aux bodies only touch walls
         stats['aux_wall_contacts'] += int((np.abs(cvel[:, [1, 3, 5, 7]]).sum(-1) > 0).sum())
         stats['torso_contacts'] += int((np.abs(cvel[:, 0]).sum(-1) > 0).sum())
+        if t == 0 and len(oenv.sys.boxes):   # envs with some capsule within its radius of a wall box right now
+            stats['wall_contact_envs'] = int(_ambiguous_contacts(oenv, s.qp, eps=np.inf, walls_only=True).any(1).sum())
         same = np.ones(n, bool)      # envs on the oracle's own branch: everything below is compared against `nxt`
         same[rest] = False
         P.assert_qp_close(got.qp, nxt.qp, f'{kind} t={t}', rows=same)

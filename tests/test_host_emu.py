@@ -108,3 +108,44 @@ def test_action_repeat_runs_more_substeps():
     oenv = oenvs.ENVS['ant'](action_repeat=2)
     s = oenv.reset(P.keys_for(n, seed=2))
     _check('ant', oenv, Emu('ant', action_repeat=2), s, 4, n, sys_factory=lambda: oenvs.ENVS['ant'](action_repeat=2).sys)
+
+
+@pytest.mark.parametrize('kind', ['ant_heavenhell', 'ant_tag', 'ant_gather'])
+def test_capsule_end_table_never_misses_a_wall_in_reach(kind):
+    """The exact cull of the lower leg's wall contacts: whenever SOME point of the capsule's segment is within the
+    capsule radius of a wall box, that wall must be listed at the tip's or at the knee's cell of the capsule-end
+    table (faces: the distance along a segment is linear, smallest at an end; vertices: the nearer end is within half
+    a segment). 200 000 random capsules thrown at the walls, incl. poses through and on top of them."""
+    emu = Emu(kind)
+    lib = emu.lib
+    lo_hi = np.zeros((8, 6), np.float32)
+    nw = lib.emu_walls(emu.h, lo_hi.ctypes.data_as(C.c_void_p))
+    boxes = lo_hi[:nw]
+    oenv = oenvs.ENVS[kind]()
+    S = oenv.sys
+    assert np.allclose(np.sort(boxes, axis=0), np.sort(S.boxes + np.array([0, 0, 0.5, 0, 0, 0.5], np.float32), axis=0), atol=1e-6)
+    rng = np.random.default_rng(7)
+    n, r = 200_000, 0.08
+    k = list(S.cap_body).index(2)
+    half = float(np.linalg.norm(S.cap_a[k] - S.cap_b[k])) / 2        # lower-leg half segment
+    # centres near a random wall's boundary (within 0.6 m), random 3-D directions
+    w = rng.integers(0, nw, n)
+    u = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    c = boxes[w, :3] + u * (boxes[w, 3:] - boxes[w, :3])
+    c[:, :2] += rng.normal(0, 0.35, (n, 2)).astype(np.float32)
+    c[:, 2] = rng.uniform(0.0, 1.3, n)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d *= half / np.linalg.norm(d, axis=1, keepdims=True)
+    a, b = (c + d).astype(np.float32), (c - d).astype(np.float32)
+    sp, bp = S._closest_segment_box(a[:, None, :].repeat(nw, 1), b[:, None, :].repeat(nw, 1), boxes[None, :, :3], boxes[None, :, 3:])
+    dist = np.sqrt(((sp - bp) ** 2).sum(-1))                          # [n, nw]
+    touching = dist < r
+    masks = np.zeros((2, n), np.uint32)
+    for i, pts in enumerate((a, b)):
+        xy = np.ascontiguousarray(pts[:, :2], np.float32)
+        assert lib.emu_tip_masks(emu.h, C.c_long(n), xy.ctypes.data_as(C.c_void_p), masks[i].ctypes.data_as(C.c_void_p)) == 0
+    listed = ((masks[0] | masks[1])[:, None] >> np.arange(nw)[None, :]) & 1
+    assert touching.sum() > 5000                                       # the sample does exercise contacts
+    assert not (touching & (listed == 0)).any(), np.argwhere(touching & (listed == 0))[:5]
+    # and the table is worth having: most capsules that touch nothing are not flagged at all
+    assert ((masks[0] | masks[1]) == 0)[~touching.any(1)].mean() > 0.3

@@ -36,6 +36,7 @@ struct DevConst {
   int32_t obs_lo, obs_out;                   // emitted columns [obs_lo, obs_lo + obs_out); obs_out == obs_dim: all
   int32_t episode_length, auto_reset, substeps, track_metrics, n_walls, has_rng;
   int32_t prefetch_ctas;                     // step kernel: L2 prefetch distance in CTAs (0: this CTA's own, harmless)
+  int32_t small_batch_envs;                  // batches up to this size run step_kernel_small (kernels.cu StepCfg)
   float h, dt, gravity_z, vel_damp, ang_damp, baumgarte, friction, elasticity;
   float m_torso, m_leg, inv_m_torso, inv_m_leg, r_torso, r_leg;
   float k_joint, sd_joint, ad_joint, ls_joint, act_strength;

@@ -1003,3 +1003,26 @@ def test_two_handles_on_two_devices():
         torch.cuda.synchronize(dev)
         outs.append((s.obs.cpu(), s.buf['qp'].cpu()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_small_batch_instantiation_is_bit_identical(monkeypatch):
+    """Batches up to 2 warps per sub-partition run `step_kernel_small` (the same source compiled for up to 255
+    registers: one warp's latency through the substeps drops ~15 %). The contact arithmetic is explicitly rounded, so
+    the two instantiations must agree bit for bit -- checked on all four families over 80 steps with short episodes
+    (cached autoreset), HeavenHell's spawn-wall contacts included. POBRAX_SMALL_BATCH_ENVS is read at create."""
+    from po_brax_b200 import envs
+    n, T = 2048, 80
+    g = torch.Generator(device='cuda').manual_seed(3)
+    acts = torch.rand((4, n, 8), device='cuda', generator=g) * 2 - 1
+    for kind in KINDS:
+        outs = []
+        for limit in ('0', '100000000'):          # never / always the small-batch instantiation
+            monkeypatch.setenv('POBRAX_SMALL_BATCH_ENVS', limit)
+            env = envs.create(kind, batch_size=n, episode_length=25)
+            s = env.reset(P.keys_for(n, seed=17))
+            for t in range(T):
+                s = env.step(s, acts[t % 4])
+            torch.cuda.synchronize()
+            outs.append({k: s.buf[k].clone() for k in ('obs', 'qp', 'reward', 'done', 'steps')})
+        for k in outs[0]:
+            assert torch.equal(outs[0][k], outs[1][k]), (kind, k)

@@ -59,7 +59,7 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
 __device__ __forceinline__ float rsqrt_ftz(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rcp_ftz(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #endif
-__device__ __forceinline__ float sqrt_pos(float x) { return x > 1e-30f ? __fmul_rn(x, rsqrt_ftz(x)) : 0.0f; }
+__device__ __forceinline__ float sqrt_pos(float x) { return x > 1e-30f ? x * rsqrt_ftz(x) : 0.0f; }
 
 struct Imp { V3 dv, dw; float hit; };  // one contact's (dvel, dang) and whether it is non-zero
 
@@ -70,21 +70,21 @@ __device__ __forceinline__ Imp impulse(V3 rel, V3 v, V3 n, float pen, float inv_
   Imp o;
   o.dv = o.dw = mk(0.f, 0.f, 0.f);
   o.hit = 0.0f;
-  const float nv = xdot(n, v);
-  const V3 t1 = xcross(rel, n);
-  const float rden = rcp_ftz(__fadd_rn(inv_m, xdot(n, xcross(t1, rel))));
-  const float J = __fmul_rn(fmaf(baumgarte, pen, -__fmul_rn(__fadd_rn(1.0f, elasticity), nv)), rden);
+  const float nv = dot(n, v);
+  const V3 t1 = cross(rel, n);
+  const float rden = rcp_ftz(inv_m + dot(n, cross(t1, rel)));
+  const float J = (baumgarte * pen - (1.0f + elasticity) * nv) * rden;
   if (!((pen > 0.0f) && (nv < 0.0f) && (J > 0.0f))) return o;
-  const V3 Jn = xscale(J, n);
-  o.dv = xscale(inv_m, Jn);
-  o.dw = xcross(rel, Jn);
-  const V3 vd = fma3(-nv, n, v);
-  const float nd = sqrt_pos(xdot(vd, vd));
+  const V3 Jn = J * n;
+  o.dv = inv_m * Jn;
+  o.dw = cross(rel, Jn);
+  const V3 vd = v - nv * n;
+  const float nd = sqrt_pos(dot(vd, vd));
   if (nd > 0.01f) {
-    const float Jd = fminf(__fmul_rn(nd, rden), __fmul_rn(friction, J));
-    const V3 Jdv = xscale(__fmul_rn(-Jd, rcp_ftz(__fadd_rn(1e-6f, nd))), vd);
-    o.dv = fma3(inv_m, Jdv, o.dv);
-    o.dw = xadd(o.dw, xcross(rel, Jdv));
+    const float Jd = fminf(nd * rden, friction * J);
+    const V3 Jdv = (-Jd * rcp_ftz(1e-6f + nd)) * vd;
+    o.dv += inv_m * Jdv;
+    o.dw += cross(rel, Jdv);
   }
   o.hit = ((o.dv.x != 0.0f) || (o.dv.y != 0.0f) || (o.dv.z != 0.0f)) ? 1.0f : 0.0f;
   return o;
@@ -95,21 +95,21 @@ __device__ __forceinline__ Imp impulse(V3 rel, V3 v, V3 n, float pen, float inv_
 // the substep loop has no divergent region for it. e = world-frame offset of the capsule end from the body.
 __device__ __forceinline__ void foot_ground(const Body& b, V3 e, float r, float inv_m, const DevConst& C, V3& dv,
                                             V3& dw) {
-  const float pen = __fsub_rn(r, __fadd_rn(b.p.z, e.z));
-  const float rx = e.x, ry = e.y, rz = __fsub_rn(e.z, r);
+  const float pen = r - (b.p.z + e.z);
+  const float rx = e.x, ry = e.y, rz = e.z - r;
   const float vx = fmaf(b.w.y, rz, fmaf(-b.w.z, ry, b.v.x));
   const float vy = fmaf(b.w.z, rx, fmaf(-b.w.x, rz, b.v.y));
   const float nv = fmaf(b.w.x, ry, fmaf(-b.w.y, rx, b.v.z));
   const float rden = rcp_ftz(fmaf(rx, rx, fmaf(ry, ry, inv_m)));
-  const float J = __fmul_rn(fmaf(C.baumgarte, pen, -__fmul_rn(__fadd_rn(1.0f, C.elasticity), nv)), rden);
+  const float J = (C.baumgarte * pen - (1.0f + C.elasticity) * nv) * rden;
   const bool apply_n = (pen > 0.0f) && (nv < 0.0f) && (J > 0.0f);
   const float Jn = apply_n ? J : 0.0f;
-  const float nd = sqrt_pos(fmaf(vx, vx, __fmul_rn(vy, vy)));  // |v_d| to ~2 ulp (feeds a min() and a 0.01 threshold)
-  const float cd = __fmul_rn(-fminf(__fmul_rn(nd, rden), __fmul_rn(C.friction, J)), rcp_ftz(__fadd_rn(1e-6f, nd)));
+  const float nd = sqrt_pos(fmaf(vx, vx, vy * vy));  // |v_d| to ~2 ulp (feeds a min() and a 0.01 threshold)
+  const float cd = -fminf(nd * rden, C.friction * J) * rcp_ftz(1e-6f + nd);
   const float c = (apply_n && nd > 0.01f) ? cd : 0.0f;
-  const float jx = __fmul_rn(c, vx), jy = __fmul_rn(c, vy);
-  dv = mk(__fmul_rn(inv_m, jx), __fmul_rn(inv_m, jy), __fmul_rn(inv_m, Jn));
-  dw = mk(fmaf(ry, Jn, -__fmul_rn(rz, jy)), fmaf(rz, jx, -__fmul_rn(rx, Jn)), fmaf(rx, jy, -__fmul_rn(ry, jx)));
+  const float jx = c * vx, jy = c * vy;
+  dv = mk(inv_m * jx, inv_m * jy, inv_m * Jn);
+  dw = mk(ry * Jn - rz * jy, rz * jx - rx * Jn, rx * jy - ry * jx);
 }
 
 // The torso's capsule_plane candidate: a sphere of radius r centred on the body (rel = (0, 0, -r)) on the ground plane
@@ -118,18 +118,18 @@ __device__ __forceinline__ void foot_ground(const Body& b, V3 e, float r, float 
 // episode, in every substep.
 __device__ __forceinline__ void torso_ground(const Body& b, float r, float inv_m, const DevConst& C, V3& dv, V3& dw) {
   dv = dw = mk(0.f, 0.f, 0.f);
-  const float pen = __fsub_rn(r, b.p.z);
+  const float pen = r - b.p.z;
   const float vx = fmaf(-r, b.w.y, b.v.x), vy = fmaf(r, b.w.x, b.v.y), nv = b.v.z;   // v + w x rel
   const float rden = rcp_ftz(inv_m);
-  const float J = __fmul_rn(fmaf(C.baumgarte, pen, -__fmul_rn(__fadd_rn(1.0f, C.elasticity), nv)), rden);
+  const float J = (C.baumgarte * pen - (1.0f + C.elasticity) * nv) * rden;
   if (!((pen > 0.0f) && (nv < 0.0f) && (J > 0.0f))) return;
-  dv.z = __fmul_rn(inv_m, J);
-  const float nd = sqrt_pos(fmaf(vx, vx, __fmul_rn(vy, vy)));
+  dv.z = inv_m * J;
+  const float nd = sqrt_pos(fmaf(vx, vx, vy * vy));
   if (nd > 0.01f) {
-    const float cd = __fmul_rn(-fminf(__fmul_rn(nd, rden), __fmul_rn(C.friction, J)), rcp_ftz(__fadd_rn(1e-6f, nd)));
-    const float jx = __fmul_rn(cd, vx), jy = __fmul_rn(cd, vy);
-    dv.x = __fmul_rn(inv_m, jx); dv.y = __fmul_rn(inv_m, jy);
-    dw = mk(__fmul_rn(r, jy), __fmul_rn(-r, jx), 0.f);          // rel x (jx, jy, 0)
+    const float cd = -fminf(nd * rden, C.friction * J) * rcp_ftz(1e-6f + nd);
+    const float jx = cd * vx, jy = cd * vy;
+    dv.x = inv_m * jx; dv.y = inv_m * jy;
+    dw = mk(r * jy, -r * jx, 0.f);          // rel x (jx, jy, 0)
   }
 }
 
@@ -142,8 +142,8 @@ __device__ __forceinline__ V3 clamp3(V3 p, V3 lo, V3 hi) {
 // (same procedure as oracle/brax_v1.py:_closest_segment_box).
 __device__ __forceinline__ float seg_box_t(V3 a, V3 d, V3 lo, V3 hi) {
   auto g = [&](float t) {
-    const V3 p = fma3(t, d, a);
-    return xdot(xsub(p, clamp3(p, lo, hi)), d);
+    const V3 p = a + t * d;
+    return dot(p - clamp3(p, lo, hi), d);
   };
   const float g0 = g(0.0f), g1 = g(1.0f);
   if (g0 >= 0.0f) return 0.0f;
@@ -151,35 +151,35 @@ __device__ __forceinline__ float seg_box_t(V3 a, V3 d, V3 lo, V3 hi) {
   float tl = 0.0f, tr = 1.0f, gl = g0, gr = g1;
 #pragma unroll 1
   for (int i = 0; i < 16; ++i) {
-    const float tm = __fmul_rn(0.5f, __fadd_rn(tl, tr));
+    const float tm = 0.5f * (tl + tr);
     const float gm = g(tm);
     if (gm > 0.0f) { tr = tm; gr = gm; } else { tl = tm; gl = gm; }
   }
-  const float den = __fsub_rn(gr, gl);
-  return den > 0.0f ? __fsub_rn(tl, __fdividef(__fmul_rn(gl, __fsub_rn(tr, tl)), den)) : tl;
+  const float den = gr - gl;
+  return den > 0.0f ? tl - gl * (tr - tl) / den : tl;
 }
 
 // A rare contact (evaluated out of line, see rare_group): capsule (segment p + e .. p - e, radius rad) vs the axis-aligned
 // Arena box [lo, hi]: one contact at the closest box point, normal (seg_pt - box_pt)/(1e-6 + d), penetration rad - d.
 __device__ __forceinline__ Imp contact_general(V3 p, V3 e, V3 v, V3 w, float rad, float inv_m, V3 lo, V3 hi,
                                                float baumgarte, float friction, float elasticity) {
-  const V3 a = xadd(p, e);
-  const V3 d = xsub(xsub(p, e), a);
+  const V3 a = p + e;
+  const V3 d = (p - e) - a;
   const float t = seg_box_t(a, d, lo, hi);
-  const V3 sp = fma3(t, d, a);
+  const V3 sp = a + t * d;
   const V3 bp = clamp3(sp, lo, hi);
-  const V3 dvec = xsub(sp, bp);
-  const float dist = sqrt_pos(xdot(dvec, dvec));
-  const float pen = __fsub_rn(rad, dist);
+  const V3 dvec = sp - bp;
+  const float dist = sqrt_pos(dot(dvec, dvec));
+  const float pen = rad - dist;
   if (!(pen > 0.0f)) {
     Imp o;
     o.dv = o.dw = mk(0.f, 0.f, 0.f);
     o.hit = 0.0f;
     return o;
   }
-  const V3 n = xscale(rcp_ftz(__fadd_rn(1e-6f, dist)), dvec);
-  const V3 rel = xsub(bp, p);
-  return impulse(rel, xadd(v, xcross(w, rel)), n, pen, inv_m, baumgarte, friction, elasticity);
+  const V3 n = rcp_ftz(1e-6f + dist) * dvec;
+  const V3 rel = bp - p;
+  return impulse(rel, v + cross(w, rel), n, pen, inv_m, baumgarte, friction, elasticity);
 }
 
 // Candidate walls of a body centred at (x, y): bit w of the byte set <=> wall w is within that body type's
@@ -260,7 +260,7 @@ __device__ __noinline__ Imp rare_group(V3 p, V3 e, V3 v, V3 w, float rad, float 
   Imp o;
   o.dv = o.dw = zero;
   o.hit = 0.0f;
-  const V3 a = xadd(p, e), b = xsub(p, e);
+  const V3 a = p + e, b = p - e;
   const V3 smin = mk(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z));
   const V3 smax = mk(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z));
   do {
@@ -273,12 +273,12 @@ __device__ __noinline__ Imp rare_group(V3 p, V3 e, V3 v, V3 w, float rad, float 
                             fmaxf(lo.z - smax.z, smin.z - hi.z));
     if (gap < rad) {
       const Imp c = contact_general(p, e, v, w, rad, inv_m, lo, hi, baumgarte, friction, elasticity);
-      o.dv = xadd(o.dv, c.dv); o.dw = xadd(o.dw, c.dw); o.hit += c.hit;
+      o.dv += c.dv; o.dw += c.dw; o.hit += c.hit;
     }
   } while (m);
   if (o.hit > 1.0f) {  // (1e-8 + 1) == 1 in float32: only a multi-contact group divides
-    const float inv = __fdividef(1.0f, __fadd_rn(1e-8f, o.hit));
-    o.dv = xscale(inv, o.dv); o.dw = xscale(inv, o.dw);
+    const float inv = 1.0f / (1e-8f + o.hit);
+    o.dv = inv * o.dv; o.dw = inv * o.dw;
   }
   return o;
 }
@@ -311,20 +311,20 @@ __device__ __forceinline__ Imp impulse_planar(V3 rel, V3 v, float nx, float ny, 
   Imp o;
   o.dv = o.dw = mk(0.f, 0.f, 0.f);
   o.hit = 0.0f;
-  const float nv = fmaf(ny, v.y, __fmul_rn(nx, v.x));
-  const V3 t1 = mk(__fmul_rn(-rel.z, ny), __fmul_rn(rel.z, nx), fmaf(rel.x, ny, -__fmul_rn(rel.y, nx)));   // rel x n
-  const float rden = rcp_ftz(__fadd_rn(inv_m, xdot(t1, t1)));            // n.((rel x n) x rel) = |rel x n|^2
-  const float J = __fmul_rn(fmaf(baumgarte, pen, -__fmul_rn(__fadd_rn(1.0f, elasticity), nv)), rden);
+  const float nv = nx * v.x + ny * v.y;
+  const V3 t1 = mk(-rel.z * ny, rel.z * nx, rel.x * ny - rel.y * nx);   // rel x n
+  const float rden = rcp_ftz(inv_m + dot(t1, t1));                       // n.((rel x n) x rel) = |rel x n|^2
+  const float J = (baumgarte * pen - (1.0f + elasticity) * nv) * rden;
   if (!((pen > 0.0f) && (nv < 0.0f) && (J > 0.0f))) return o;
-  o.dv = mk(__fmul_rn(inv_m, __fmul_rn(J, nx)), __fmul_rn(inv_m, __fmul_rn(J, ny)), 0.f);
-  o.dw = xscale(J, t1);
-  const V3 vd = mk(fmaf(-nv, nx, v.x), fmaf(-nv, ny, v.y), v.z);
-  const float nd = sqrt_pos(xdot(vd, vd));
+  o.dv = mk(inv_m * (J * nx), inv_m * (J * ny), 0.f);
+  o.dw = J * t1;
+  const V3 vd = mk(v.x - nv * nx, v.y - nv * ny, v.z);
+  const float nd = sqrt_pos(dot(vd, vd));
   if (nd > 0.01f) {
-    const float Jd = fminf(__fmul_rn(nd, rden), __fmul_rn(friction, J));
-    const V3 Jdv = xscale(__fmul_rn(-Jd, rcp_ftz(__fadd_rn(1e-6f, nd))), vd);
-    o.dv = fma3(inv_m, Jdv, o.dv);
-    o.dw = xadd(o.dw, xcross(rel, Jdv));
+    const float Jd = fminf(nd * rden, friction * J);
+    const V3 Jdv = (-Jd * rcp_ftz(1e-6f + nd)) * vd;
+    o.dv += inv_m * Jdv;
+    o.dw += cross(rel, Jdv);
   }
   o.hit = 1.0f;
   return o;
@@ -342,20 +342,19 @@ __device__ __forceinline__ bool tip_wall(const Body& b, V3 e, float rad, float i
   if (m & (m - 1u)) return false;
   const int k = __ffs(m) - 1;
   const float4 l4 = C.wall_box[k][0], h4 = C.wall_box[k][1];
-  const V3 F = xadd(b.p, e);
+  const V3 F = b.p + e;
   const V3 bp = clamp3(F, mk(l4.x, l4.y, l4.z), mk(h4.x, h4.y, h4.z));
-  const float dx = __fsub_rn(F.x, bp.x), dy = __fsub_rn(F.y, bp.y);
-  if (F.z != bp.z || fmaf(dy, e.y, __fmul_rn(dx, e.x)) > 0.0f) return false;
+  const float dx = F.x - bp.x, dy = F.y - bp.y;
+  if (F.z != bp.z || dx * e.x + dy * e.y > 0.0f) return false;
   c.dv = c.dw = mk(0.f, 0.f, 0.f);
   c.hit = 0.0f;
-  const float d2 = fmaf(dy, dy, __fmul_rn(dx, dx)), rs = __fadd_rn(rad, 1e-6f);
-  if (d2 < __fmul_rn(rs, rs)) {
+  const float d2 = dx * dx + dy * dy, rs = rad + 1e-6f;
+  if (d2 < rs * rs) {
     const float dist = sqrt_pos(d2);
-    const float pen = __fsub_rn(rad, dist);
-    const float inv = rcp_ftz(__fadd_rn(1e-6f, dist));
-    const V3 rel = xsub(bp, b.p);
-    c = impulse_planar(rel, xadd(b.v, xcross(b.w, rel)), __fmul_rn(inv, dx), __fmul_rn(inv, dy), pen, inv_m, C.baumgarte,
-                       C.friction, C.elasticity);
+    const float pen = rad - dist;
+    const float inv = rcp_ftz(1e-6f + dist);
+    const V3 rel = bp - b.p;
+    c = impulse_planar(rel, b.v + cross(b.w, rel), inv * dx, inv * dy, pen, inv_m, C.baumgarte, C.friction, C.elasticity);
   }
   return true;
 }

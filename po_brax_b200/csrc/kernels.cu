@@ -37,11 +37,12 @@ template <int KIND> struct StepCfg {
 #endif
   static constexpr int envs = threads / 4;
   static constexpr int min_blocks = (KIND == POBRAX_ANT ? POBRAX_ANT_WARPS_PER_SMSP : POBRAX_WALL_WARPS_PER_SMSP) * (128 / threads);  // 96 / 128 registers
-  // The small-batch ("latency") instantiation: compiled for 2 resident warps per sub-partition, i.e. up to 255
-  // registers -- no spills, a freer schedule. Below one warp per sub-partition a step is bound by ONE warp's latency
-  // through the substeps, and that drops 14-16 % (HeavenHell 128 envs 14.8 -> 12.7 us, Ant 4 096 10.2 -> 8.6 us); from
-  // ~16 k envs on the throughput build wins. Same source, and the contact arithmetic is explicitly rounded, so
-  // the two instantiations agree bit for bit (GPU-tested).
+  // The small-batch instantiation (step_kernel<KIND, true>): compiled for 2 resident warps per sub-partition, i.e. up
+  // to 255 registers -- no spills, a freer schedule. Below one warp per sub-partition a step is bound by ONE warp's
+  // latency through the substeps, and that drops ~15 % (HeavenHell 128 envs 14.8 -> 12.4 us, Ant 4 096 10.2 -> 8.6 us);
+  // from ~16 k envs on the throughput build wins. Same PTX for both; the inline code comes out of ptxas with the same
+  // arithmetic and the out-of-line contact group is one shared function, so the two agree bit for bit
+  // (tests/test_gpu_parity.py::test_small_batch_instantiation_is_bit_identical guards that).
   static constexpr int min_blocks_lat = 2 * (128 / threads);
 };
 
@@ -201,27 +202,14 @@ __device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, const fl
 }
 
 // --------------------------------------------------------------------------------------------- step
-template <int KIND, bool LAT>
-__device__ __forceinline__ void step_body(const DevConst& C, const PobraxState& S, const float* __restrict__ action);
-
-template <int KIND>
+// SMALL = the small-batch instantiation (StepCfg::min_blocks_lat): same text, compiled for up to 255 registers.
+template <int KIND, bool SMALL>
 #ifdef POBRAX_TUNE_MAXNREG   // tuning builds: cap the wall variants' registers directly
 __global__ void __launch_bounds__(StepCfg<KIND>::threads) __maxnreg__(KIND == POBRAX_ANT ? 96 : POBRAX_TUNE_MAXNREG)
 #else
-__global__ void __launch_bounds__(StepCfg<KIND>::threads, StepCfg<KIND>::min_blocks)
+__global__ void __launch_bounds__(StepCfg<KIND>::threads, SMALL ? StepCfg<KIND>::min_blocks_lat : StepCfg<KIND>::min_blocks)
 #endif
 step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float* __restrict__ action) {
-  step_body<KIND, false>(C, S, action);
-}
-
-template <int KIND>
-__global__ void __launch_bounds__(StepCfg<KIND>::threads, StepCfg<KIND>::min_blocks_lat)
-step_kernel_small(const __grid_constant__ DevConst C, const PobraxState S, const float* __restrict__ action) {
-  step_body<KIND, true>(C, S, action);
-}
-
-template <int KIND, bool LAT>
-__device__ __forceinline__ void step_body(const DevConst& C, const PobraxState& S, const float* __restrict__ action) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int leg = lane & 3, es = lane >> 2;
@@ -861,15 +849,15 @@ static cudaError_t setup_device_t(DevConst& C, size_t smem_limit, const char** w
   if (rs > smem_limit) { *what = "reset kernel: observation staging + object grid exceed the device's shared memory per block (smaller cage_xy?)"; return cudaErrorInvalidValue; }
   cudaError_t e;
   *what = "cudaFuncSetAttribute(step_kernel, MaxDynamicSharedMemorySize)";
-  if ((e = cudaFuncSetAttribute(step_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(step_kernel_small<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(step_kernel<KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(step_kernel<KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss)) != cudaSuccess) return e;
   *what = "cudaFuncSetAttribute(reset_kernel, MaxDynamicSharedMemorySize)";
   if ((e = cudaFuncSetAttribute(reset_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs)) != cudaSuccess) return e;
   int dev = 0, sms = 148, per_sm = StepCfg<KIND>::min_blocks;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   *what = "cudaOccupancyMaxActiveBlocksPerMultiprocessor(step_kernel)";
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<KIND>, StepCfg<KIND>::threads, ss)) != cudaSuccess) return e;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<KIND, false>, StepCfg<KIND>::threads, ss)) != cudaSuccess) return e;
   const char* ov = getenv("POBRAX_PREFETCH_CTAS");
   C.prefetch_ctas = ov ? atoi(ov) : sms * per_sm;
   // batches up to 2 warps per sub-partition run the small-batch instantiation (POBRAX_SMALL_BATCH_ENVS overrides:
@@ -894,9 +882,9 @@ template <int KIND>
 static cudaError_t launch_step_t(const DevConst& C, const PobraxState& S, const float* action, cudaStream_t st) {
   const int blocks = (C.n_envs + StepCfg<KIND>::envs - 1) / StepCfg<KIND>::envs;
   if (C.n_envs <= C.small_batch_envs)
-    step_kernel_small<KIND><<<blocks, StepCfg<KIND>::threads, step_smem_bytes<KIND>(C), st>>>(C, S, action);
+    step_kernel<KIND, true><<<blocks, StepCfg<KIND>::threads, step_smem_bytes<KIND>(C), st>>>(C, S, action);
   else
-    step_kernel<KIND><<<blocks, StepCfg<KIND>::threads, step_smem_bytes<KIND>(C), st>>>(C, S, action);
+    step_kernel<KIND, false><<<blocks, StepCfg<KIND>::threads, step_smem_bytes<KIND>(C), st>>>(C, S, action);
   return cudaGetLastError();
 }
 

@@ -19,17 +19,6 @@ __host__ __device__ __forceinline__ V3 cross(V3 a, V3 b) {
   return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 
-// Explicitly rounded forms for the contact code (ant_physics.cuh): every product and sum is pinned -- fmaf or an .rn
-// intrinsic, nothing left for NVVM / ptxas to contract or not -- so that differently scheduled builds of the step
-// kernels (the throughput and the small-batch instantiation) produce the same bits.
-__device__ __forceinline__ float xdot(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, __fmul_rn(a.x, b.x))); }
-__device__ __forceinline__ V3 xcross(V3 a, V3 b) {
-  return mk(fmaf(a.y, b.z, -__fmul_rn(a.z, b.y)), fmaf(a.z, b.x, -__fmul_rn(a.x, b.z)), fmaf(a.x, b.y, -__fmul_rn(a.y, b.x)));
-}
-__device__ __forceinline__ V3 xscale(float s, V3 a) { return mk(__fmul_rn(s, a.x), __fmul_rn(s, a.y), __fmul_rn(s, a.z)); }
-__device__ __forceinline__ V3 xadd(V3 a, V3 b) { return mk(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z)); }
-__device__ __forceinline__ V3 xsub(V3 a, V3 b) { return mk(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)); }
-
 // One rigid body of brax.QP: pos, rot (w,x,y,z), vel, ang.
 struct Body { V3 p; float qw, qx, qy, qz; V3 v, w; };
 

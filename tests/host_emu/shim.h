@@ -10,11 +10,6 @@
 
 #include "../../po_brax_b200/csrc/dev_const.h"
 
-// round-to-nearest single operations (-ffp-contract=off: a product and a sum are never fused by g++)
-inline float __fmul_rn(float a, float b) { return a * b; }
-inline float __fadd_rn(float a, float b) { return a + b; }
-inline float __fsub_rn(float a, float b) { return a - b; }
-
 namespace pobrax {
 
 struct F2 { unsigned long long v; };

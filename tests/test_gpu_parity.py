@@ -1006,10 +1006,11 @@ def test_two_handles_on_two_devices():
 
 
 def test_small_batch_instantiation_is_bit_identical(monkeypatch):
-    """Batches up to 2 warps per sub-partition run `step_kernel_small` (the same source compiled for up to 255
-    registers: one warp's latency through the substeps drops ~15 %). The contact arithmetic is explicitly rounded, so
-    the two instantiations must agree bit for bit -- checked on all four families over 80 steps with short episodes
-    (cached autoreset), HeavenHell's spawn-wall contacts included. POBRAX_SMALL_BATCH_ENVS is read at create."""
+    """Batches up to 2 warps per sub-partition run `step_kernel<KIND, true>` (the same source compiled for up to 255
+    registers: one warp's latency through the substeps drops ~15 %). Results must not depend on which instantiation
+    ran -- a shard must equal its slice of a larger batch -- so the two are held bit for bit against each other on all
+    four families over 80 steps with short episodes (cached autoreset), HeavenHell's spawn-wall contacts included.
+    POBRAX_SMALL_BATCH_ENVS is read at create."""
     from po_brax_b200 import envs
     n, T = 2048, 80
     g = torch.Generator(device='cuda').manual_seed(3)

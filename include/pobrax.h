@@ -128,6 +128,13 @@ int pobrax_draw_arena(PobraxParams* p, float cage_x, float cage_y, float half_he
 int pobrax_draw_t_maze(PobraxParams* p, float t_x, float t_y, float hallway_width, float half_height);
 int pobrax_layout(const PobraxParams* p, PobraxLayout* out);
 
+/* Validates *p, builds the per-handle constants (wall boxes, candidate-wall tables behind texture objects, Gather
+ * grid) on `device` and sets up the kernels for that device (dynamic shared-memory limits, occupancy): a process may
+ * hold handles on several GPUs. Fails with a message (pobrax_last_error) when e.g. the observation staging + Gather
+ * grid exceed the device's shared memory per block. Tuning knobs read here from the environment (never needed for
+ * correctness): POBRAX_PREFETCH_CTAS (L2 prefetch distance of the step kernel), POBRAX_SMALL_BATCH_ENVS (batches up to
+ * this size run the small-batch instantiation of the step kernel -- same results bit for bit; default 2 warps per SM
+ * sub-partition = 9 472 envs on a B200; 0 = never). */
 int pobrax_create(const PobraxParams* p, int device, void** handle);
 int pobrax_destroy(void* handle);
 

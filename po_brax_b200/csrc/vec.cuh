@@ -27,7 +27,18 @@ struct Body { V3 p; float qw, qx, qy, qz; V3 v, w; };
 // (pk(s, s) -> the .F32 operand form) and half swaps into the instruction's operand modifiers, and packing two
 // freshly computed scalars is free (they are allocated as a pair). Every operation rounds exactly like its scalar
 // counterpart (fma.rn / add.rn / mul.rn per half).
-#ifndef POBRAX_HOST_EMU   // (the g++ build of tests/host_emu supplies F2 and these primitives from its own shim header)
+#if defined(POBRAX_TUNE_SCALAR_F2)   // tuning builds: the same text on scalar FFMA / FADD / FMUL
+struct F2 { float l, h; };
+__device__ __forceinline__ F2 pk(float lo, float hi) { F2 r; r.l = lo; r.h = hi; return r; }
+__device__ __forceinline__ F2 bc(float s) { return pk(s, s); }
+__device__ __forceinline__ float lo(F2 a) { return a.l; }
+__device__ __forceinline__ float hi(F2 a) { return a.h; }
+__device__ __forceinline__ F2 neg(F2 a) { return pk(-a.l, -a.h); }
+__device__ __forceinline__ F2 operator+(F2 a, F2 b) { return pk(a.l + b.l, a.h + b.h); }
+__device__ __forceinline__ F2 operator-(F2 a, F2 b) { return pk(a.l - b.l, a.h - b.h); }
+__device__ __forceinline__ F2 operator*(F2 a, F2 b) { return pk(a.l * b.l, a.h * b.h); }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) { return pk(fmaf(a.l, b.l, c.l), fmaf(a.h, b.h, c.h)); }
+#elif !defined(POBRAX_HOST_EMU)   // (the g++ build of tests/host_emu supplies F2 and these primitives from its own shim header)
 struct F2 { unsigned long long v; };
 __device__ __forceinline__ F2 pk(float lo, float hi) { F2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ F2 bc(float s) { return pk(s, s); }

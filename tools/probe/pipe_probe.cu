@@ -1,0 +1,98 @@
+// Issue / FMA-pipe probe for sm_100a: how many warp-instructions per clock one SM sub-partition sustains for scalar
+// FFMA, packed FFMA2 / FMUL2 / FADD2 and mixes with ALU-pipe work, as a function of resident warps per sub-partition
+// and of the independent chains (ILP) inside a warp. Feeds the "two envs per lane, everything packed" design question:
+// does a packed-only instruction stream reach the FMA pipe's rate with 2 warps per sub-partition?
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pipe_probe pipe_probe.cu && ./pipe_probe
+#include <cstdio>
+#include <cuda_runtime.h>
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) { u64 d; asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) { u64 d; asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float ffma(float a, float b, float c) { float d; asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+__device__ __forceinline__ float fmnmx(float a, float b) { float d; asm volatile("min.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
+__device__ __forceinline__ float fmul(float a, float b) { float d; asm volatile("mul.rn.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
+__device__ __forceinline__ unsigned lop(unsigned a, unsigned b) { unsigned d; asm volatile("xor.b32 %0, %1, %2;\n\tadd.u32 %0, %0, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ u64 pack(float x, float y) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+
+// MODE 0: scalar FFMA x ILP          1: FFMA2 x ILP          2: FMUL2 / FADD2 alternating x ILP
+//      3: FFMA2 x ILP + FMNMX x ILP/2 (ALU pipe)   4: FFMA2 x ILP/2 + FFMA x ILP/2      5: FFMA x ILP + FMNMX x ILP/2
+//      6: FFMA2 whose b operand differs per chain (3 distinct 64-bit register operands, no reuse)
+template <int MODE, int ILP>
+__global__ void k(float* out, int iters, float a0, float b0) {
+  const float t = threadIdx.x * 1e-9f;
+  u64 x[ILP], a = pack(a0 + t, a0 - t), b = pack(b0 + t, b0 - t);
+  float s[ILP], m[ILP], sa = a0 + t, sb = b0 + t;
+  u64 bb[ILP];
+  unsigned q[ILP], qa = threadIdx.x * 2654435761u;
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) { x[j] = pack(t + j, t - j); s[j] = t + j; m[j] = t * j; q[j] = threadIdx.x + j; bb[j] = pack(b0 + j * t, b0 - j * t); }
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int j = 0; j < ILP; ++j) {
+        if (MODE == 0) s[j] = ffma(s[j], sa, sb);
+        if (MODE == 1) x[j] = ffma2(x[j], a, b);
+        if (MODE == 2) x[j] = (u & 1) ? fadd2(x[j], b) : fmul2(x[j], a);
+        if (MODE == 3) { x[j] = ffma2(x[j], a, b); if (j & 1) m[j] = fmnmx(m[j], sb); }
+        if (MODE == 4) { if (j & 1) x[j] = ffma2(x[j], a, b); else s[j] = ffma(s[j], sa, sb); }
+        if (MODE == 5) { s[j] = ffma(s[j], sa, sb); if (j & 1) m[j] = fmnmx(m[j], sb); }
+        if (MODE == 6) x[j] = ffma2(x[j], bb[(j + 1) % ILP], bb[j]);
+        if (MODE == 7) x[j] = fmul2(x[j], a);
+        if (MODE == 8) x[j] = fadd2(x[j], b);
+        if (MODE == 9) x[j] = fmul2(x[j], bb[j]);
+        if (MODE == 10) s[j] = fmul(s[j], sa);
+        if (MODE == 11) { x[j] = ffma2(x[j], a, b); q[j] = lop(q[j], qa); }
+        if (MODE == 12) { if (j < ILP / 2) x[j] = ffma2(x[j], a, b); else s[j] = ffma(s[j], sa, sb); }   // blocks of ILP/2
+        if (MODE == 13) { x[j] = fmul2(x[j], a); q[j] = lop(q[j], qa); }
+        if (MODE == 14) { s[j] = ffma(s[j], sa, sb); q[j] = lop(q[j], qa); }
+      }
+    }
+  }
+  u64 r = 0; float f = 0;
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) { r ^= x[j] + q[j]; f += s[j] + m[j]; }
+  if (r == 123456789ull || f == 123.456f) out[threadIdx.x] = 1.0f;
+}
+
+template <int MODE, int ILP>
+void run(const char* name, float* out, int warps_per_smsp, double fp_per_thread_iter, double instr_per_thread_iter) {
+  const int threads = 32 * 4 * warps_per_smsp, blocks = 148, iters = 8192;   // one CTA per SM
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int r = 0; r < 4; ++r) {
+    cudaEventRecord(e0);
+    k<MODE, ILP><<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1); if (r) best = ms < best ? ms : best;
+  }
+  const double thr = (double)blocks * threads * iters;
+  printf("%-34s ILP %2d warps/SMSP %d: %7.3f ms  %6.1f TFLOP/s  %.3f warp-instr/clk/SMSP (1.92 GHz)\n", name, ILP, warps_per_smsp, best,
+         thr * fp_per_thread_iter * 2.0 / best / 1e9, thr / 32 * instr_per_thread_iter / (best * 1e-3) / 1.92e9 / (148 * 4));
+}
+
+int main() {
+  float* out; cudaMalloc(&out, 4096);
+  for (int w = 2; w <= 4; w *= 2) {
+    run<0, 4>("FFMA scalar", out, w, 8 * 4, 8 * 4);
+    run<0, 8>("FFMA scalar", out, w, 8 * 8, 8 * 8);
+    run<1, 2>("FFMA2", out, w, 8 * 2 * 2, 8 * 2);
+    run<1, 4>("FFMA2", out, w, 8 * 4 * 2, 8 * 4);
+    run<1, 8>("FFMA2", out, w, 8 * 8 * 2, 8 * 8);
+    run<6, 8>("FFMA2 3 distinct operands", out, w, 8 * 8 * 2, 8 * 8);
+    run<2, 8>("FMUL2/FADD2 (flops = 1/op)", out, w, 8 * 8 * 2 / 2.0, 8 * 8);
+    run<3, 8>("FFMA2 + 1/4 FMNMX3", out, w, 8 * 8 * 2, 8 * 10);
+    run<4, 8>("1/2 FFMA2 + 1/2 FFMA", out, w, 8 * (4 * 2 + 4), 8 * 8);
+    run<5, 8>("FFMA + 1/4 FMNMX3", out, w, 8 * 8, 8 * 10);
+    run<7, 8>("FMUL2 (1 reused operand)", out, w, 8 * 8, 8 * 8);
+    run<8, 8>("FADD2 (1 reused operand)", out, w, 8 * 8, 8 * 8);
+    run<9, 8>("FMUL2 2 distinct operands", out, w, 8 * 8, 8 * 8);
+    run<10, 8>("FMUL scalar", out, w, 8 * 4, 8 * 8);
+    run<11, 8>("FFMA2 + 2 ALU", out, w, 8 * 8 * 2, 8 * 24);
+    run<12, 8>("4 FFMA2 then 4 FFMA", out, w, 8 * (4 * 2 + 4), 8 * 8);
+    run<13, 8>("FMUL2 + 2 ALU", out, w, 8 * 8, 8 * 24);
+    run<14, 8>("FFMA + 2 ALU", out, w, 8 * 8, 8 * 24);
+  }
+  return 0;
+}

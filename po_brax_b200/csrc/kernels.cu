@@ -129,8 +129,22 @@ __device__ __forceinline__ void stage_common_obs(float* row, const Rig& r, const
   ca[b] = clip1(acc.Bw.x); ca[b + 1] = clip1(acc.Bw.y); ca[b + 2] = clip1(acc.Bw.z);
 }
 
-// AntGatherEnv._get_readings (ant_gather.py:152-181) for this lane's objects (4 per lane), written in
-// object order 0..n-1 (sequential-scatter semantics: last writer wins, -1 wraps to the last bin).
+// One object of AntGatherEnv._get_readings (ant_gather.py:152-181): its reading bin (n_read = "no write"; index -1
+// wraps to the last reading, bombs are offset by n_apples) and intensity. Out of line, one copy: four inlined copies
+// of the precise divisions and the atan2 cost the Gather kernel ~4 % (instruction fetch: ncu showed 0.76 "no
+// instruction" stall cycles per issue against 0.13 for Tag), and this code runs once per env step.
+__device__ __noinline__ float2 gather_bin(float ox, float oy, float dist, float ori, int is_bomb, int n_apples, int n_read,
+                                          float half_span, float sensor_range, float bin_res) {
+  const float ang = __fsub_rn(atan2_fast(ox, oy), ori);
+  const bool valid = (fabsf(ang) <= half_span) && (dist <= sensor_range);
+  int bin = valid ? (int)__fdiv_rn(__fadd_rn(ang, half_span), bin_res) : -1;
+  if (is_bomb && bin >= 0) bin += n_apples;
+  const float inten = bin >= 0 ? __fsub_rn(1.0f, __fdiv_rn(dist, sensor_range)) : 0.0f;
+  return make_float2(__int_as_float(bin < 0 ? bin + n_read : bin), inten);
+}
+
+// AntGatherEnv._get_readings for this lane's objects (4 per lane), written in object order 0..n-1
+// (sequential-scatter semantics: last writer wins).
 __device__ __forceinline__ void gather_readings(float* readings, const Body& T, const float (*obj)[3], const float* dist,
                                                 int leg, const DevConst& C) {
   // ori = atan2 of the torso x-axis projected on xy: (q (0,1,0,0) q^-1)[1:3]
@@ -149,12 +163,10 @@ __device__ __forceinline__ void gather_readings(float* readings, const Body& T, 
     bins[i] = n_read;  // "no write"
     inten[i] = 0.0f;
     if (kobj < n_obj) {
-      const float ang = __fsub_rn(atan2_fast(obj[i][0], obj[i][1]), ori);
-      const bool valid = (fabsf(ang) <= C.half_span) && (dist[i] <= C.sensor_range);
-      int bin = valid ? (int)__fdiv_rn(__fadd_rn(ang, C.half_span), C.bin_res) : -1;
-      if (kobj >= C.n_apples && bin >= 0) bin += C.n_apples;
-      inten[i] = bin >= 0 ? __fsub_rn(1.0f, __fdiv_rn(dist[i], C.sensor_range)) : 0.0f;
-      bins[i] = bin < 0 ? bin + n_read : bin;  // index -1 wraps to the last reading
+      const float2 b = gather_bin(obj[i][0], obj[i][1], dist[i], ori, kobj >= C.n_apples, C.n_apples, n_read, C.half_span,
+                                  C.sensor_range, C.bin_res);
+      bins[i] = __float_as_int(b.x);
+      inten[i] = b.y;
     }
   }
   for (int turn = 0; turn < 4; ++turn) {  // ordered scatter: object 0 first, object n-1 last
@@ -171,6 +183,27 @@ __device__ __forceinline__ void gather_readings(float* readings, const Body& T, 
 // Coalesced write of the warp's 8 staged observation rows (contiguous in obs[N][D]; 8*D floats start at a
 // 16-byte boundary because env0 is a multiple of 8). Rows in `first_mask` are then overwritten from the cached
 // first_obs (rare), rows in `skip_mask` are left untouched (reset_where_done).
+// The uncommon parts, out of line (one copy per library, keeps the step kernels' instruction footprint down): `copy` = the
+// column-subset / skip-mask row copy, then the rewrite of the rows in `first_mask` from the cached first_obs.
+__device__ __noinline__ void write_obs_rows_general(float* __restrict__ dst, const float* __restrict__ first,
+                                                    const float* stage, int D, int lo, int Do, int rows, unsigned first_mask,
+                                                    unsigned skip_mask, int lane, int copy) {
+  if (copy) {
+    for (int es = 0; es < rows; ++es)
+      if (!((skip_mask >> es) & 1u))
+#pragma unroll 1
+        for (int c = lane; c < Do; c += 32) dst[es * Do + c] = stage[es * D + lo + c];
+  }
+  if (first_mask != 0u) {
+    __syncwarp();
+    for (int es = 0; es < rows; ++es)
+      if ((first_mask >> es) & 1u)
+#pragma unroll 1
+        for (int c = lane; c < Do; c += 32) dst[es * Do + c] = first[es * Do + c];
+  }
+}
+
+template <bool OUTLINE>   // OUTLINE: the uncommon parts through write_obs_rows_general (Gather's step kernel)
 __device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, const float* __restrict__ first_obs,
                                                const float* stage, int D, int lo, int Do, long long env0, int n_envs,
                                                unsigned first_mask, unsigned skip_mask, int lane) {
@@ -178,7 +211,8 @@ __device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, const fl
   const int rows = (int)min((long long)8, (long long)n_envs - env0);
   if (rows <= 0) return;
   float* dst = obs + env0 * Do;
-  if (skip_mask == 0u && Do == D) {
+  const bool fast = skip_mask == 0u && Do == D;
+  if (fast) {
     const int n4 = (rows * D) >> 2;
     const float4* s4 = reinterpret_cast<const float4*>(stage);
     float4* d4 = reinterpret_cast<float4*>(dst);
@@ -186,7 +220,14 @@ __device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, const fl
     for (int i = lane; i < n4; i += 32) d4[i] = s4[i];   // unrolled: 4 LDS.128 in flight before the first STG.128
 #pragma unroll 1
     for (int i = 4 * n4 + lane; i < rows * D; i += 32) dst[i] = stage[i];
-  } else {
+  }
+  if (OUTLINE) {
+    if (!fast || first_mask != 0u)
+      write_obs_rows_general(dst, first_obs ? first_obs + env0 * Do : nullptr, stage, D, lo, Do, rows, first_mask, skip_mask,
+                             lane, fast ? 0 : 1);
+    return;
+  }
+  if (!fast) {
     for (int es = 0; es < rows; ++es)
       if (!((skip_mask >> es) & 1u))
 #pragma unroll 1
@@ -238,9 +279,10 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
     if (KIND == POBRAX_ANT_TAG) { prefetch_l2(S.aux + 2 * n + e); prefetch_l2(S.aux + 3 * n + e); }
   }
   if (KIND == POBRAX_ANT_GATHER) {  // the lane's 4 objects (read behind the loop)
-#pragma unroll
-    for (int i = 0; i < 12; ++i)
-      if (12 * leg + i < 3 * (C.n_apples + C.n_bombs)) prefetch_l2(S.aux + (size_t)(12 * leg + i) * n + e);
+    const int n_pl = min(12, 3 * (C.n_apples + C.n_bombs) - 12 * leg);
+    const float* pa = S.aux + (size_t)(12 * leg) * n + e;
+#pragma unroll 1
+    for (int i = 0; i < n_pl; ++i, pa += n) prefetch_l2(pa);
   }
   // DRAM -> L2 prefetch of the state a CTA `prefetch_ctas` further on will load (CTAs start roughly in index
   // order): its prologue then waits for an L2 hit instead of a DRAM access.
@@ -398,22 +440,27 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
     }
     __syncwarp();
     gather_readings(row + extra, r.T, obj, dist, leg, C);  // obs uses the pre-pickup object positions
+    // pickup (ant_gather.py:133-141): objects within catch_range move to the waiting area. Masks first, then a ROLLED
+    // store loop -- pickups are rare and the unrolled form was 250 instructions of a kernel that has to fit the
+    // instruction cache.
+    unsigned in_mask = 0u;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int ko = 4 * leg + i;
       if (ko < n_obj) {
         const bool in = dist[i] <= C.catch_range;
-        if (in) {
-          if (ko < C.n_apples) ++caught_a; else ++caught_b;
-          obj[i][0] = C.waiting[0]; obj[i][1] = C.waiting[1]; obj[i][2] = C.waiting[2];
-          if (valid) {
-            S.aux[(size_t)(3 * ko) * n + e] = obj[i][0];
-            S.aux[(size_t)(3 * ko + 1) * n + e] = obj[i][1];
-            S.aux[(size_t)(3 * ko + 2) * n + e] = obj[i][2];
-          }
-        }
-        all_wait &= (obj[i][0] == C.waiting[0] && obj[i][1] == C.waiting[1] && obj[i][2] == C.waiting[2]) ? 1 : 0;
+        in_mask |= in ? 1u << i : 0u;
+        if (in) { if (ko < C.n_apples) ++caught_a; else ++caught_b; }
+        all_wait &= (in || (obj[i][0] == C.waiting[0] && obj[i][1] == C.waiting[1] && obj[i][2] == C.waiting[2])) ? 1 : 0;
       }
+    }
+    if (valid && in_mask != 0u) {
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i)
+        if ((in_mask >> i) & 1u) {
+          float* o = S.aux + (size_t)(3 * (4 * leg + i)) * n + e;
+          o[0] = C.waiting[0]; o[n] = C.waiting[1]; o[2 * n] = C.waiting[2];
+        }
     }
     caught_a = quad_isum(caught_a); caught_b = quad_isum(caught_b); all_wait = quad_and(all_wait);
     reward = dead > 0.0f ? C.dying_cost : 0.0f;
@@ -470,7 +517,7 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
   unsigned fm8 = 0;
   for (int i = 0; i < 8; ++i) fm8 |= ((first_mask >> (4 * i)) & 1u) << i;
   __syncwarp();
-  write_obs_rows(S.obs, S.first_obs, stage, D, C.obs_lo, C.obs_out, env0, C.n_envs, fm8, 0u, lane);
+  write_obs_rows<KIND == POBRAX_ANT_GATHER>(S.obs, S.first_obs, stage, D, C.obs_lo, C.obs_out, env0, C.n_envs, fm8, 0u, lane);
 }
 
 // -------------------------------------------------------------------------------------------- reset
@@ -714,8 +761,8 @@ reset_kernel(const __grid_constant__ DevConst C, const PobraxState S, const uint
   unsigned sk8 = 0;
   for (int i = 0; i < 8; ++i) sk8 |= ((skip >> (4 * i)) & 1u) << i;
   __syncwarp();
-  write_obs_rows(S.obs, S.obs, stage, D, C.obs_lo, C.obs_out, env0, C.n_envs, 0u, sk8, lane);
-  if (!only_done && S.first_obs) write_obs_rows(S.first_obs, S.obs, stage, D, C.obs_lo, C.obs_out, env0, C.n_envs, 0u, sk8, lane);
+  write_obs_rows<false>(S.obs, S.obs, stage, D, C.obs_lo, C.obs_out, env0, C.n_envs, 0u, sk8, lane);
+  if (!only_done && S.first_obs) write_obs_rows<false>(S.first_obs, S.obs, stage, D, C.obs_lo, C.obs_out, env0, C.n_envs, 0u, sk8, lane);
 }
 
 // --------------------------------------------------------------------------- brax.QP <-> packed state

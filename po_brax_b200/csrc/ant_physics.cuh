@@ -225,7 +225,9 @@ struct Rig { Body T, A, B; };                 // one lane: torso replica + its l
 // Info.contact accumulators of the lane: the foot's (hot) live in registers; the torso's and the Aux body's
 // (torso-ground and wall contacts only) accumulate straight into the env's staged observation row in shared
 // memory (cv / ca = the row's contact.vel / contact.ang blocks, [nb][3] each), clipped when the row is finalised.
-struct ContactAcc { V3 Bv, Bw; float* cv; float* ca; };
+// psi: the (hip, ankle) joint angles of the substep just run -- the rotations do not change behind the joint math, so
+// after the last substep these are the observation's joint angles (the step kernel does not compute them again).
+struct ContactAcc { V3 Bv, Bw; float* cv; float* ca; F2 psi; };
 
 __device__ __forceinline__ void row_add(float* base, int body, V3 a) {
   base[3 * body] += a.x; base[3 * body + 1] += a.y; base[3 * body + 2] += a.z;
@@ -454,8 +456,9 @@ __device__ __forceinline__ F2 atan2_fast2(F2 y, F2 x) {
 // limit_and_actuator for (hip, ankle): lim_lo / lim_hi = the two joints' limits, act_h = h * strength * action.
 // dang = min(hi - psi, 0) + max(lo - psi, 0) is the limit violation (exactly 0 inside the limits), and the
 // actuator torque is cut off whenever it is non-zero.
-__device__ __forceinline__ F2 limit_and_actuator2(F2 sin_psi, F2 cos_psi, F2 lim_lo, F2 lim_hi, F2 act_h, float h_ls) {
-  const F2 psi = atan2_fast2(sin_psi, cos_psi);
+__device__ __forceinline__ F2 limit_and_actuator2(F2 sin_psi, F2 cos_psi, F2 lim_lo, F2 lim_hi, F2 act_h, float h_ls,
+                                                  F2& psi) {
+  psi = atan2_fast2(sin_psi, cos_psi);
   const F2 a = lim_hi - psi, b = lim_lo - psi;
   const F2 dang = pk(fminf(lo(a), 0.0f), fminf(hi(a), 0.0f)) + pk(fmaxf(lo(b), 0.0f), fmaxf(hi(b), 0.0f));
   const F2 t = pk(lo(dang) == 0.0f ? lo(act_h) : 0.0f, hi(dang) == 0.0f ? hi(act_h) : 0.0f);
@@ -572,7 +575,7 @@ __device__ __forceinline__ void substep2(Rig2& r, const LegK& k, const LegK2& k2
   const V3 axA = lo3(ax), axB = hi3(ax);
   const V3 nA = k.axs * cA0 - k.axc * cA1;
   const F2 s = limit_and_actuator2(pk(dot(cA0, cT.c1), dot(cB2, nA)), pk(dot(cA0, cT.c0), dot(cA2, cB2)), k2.lim_lo,
-                                   k2.lim_hi, k2.act_h, C.h_ls);
+                                   k2.lim_hi, k2.act_h, C.h_ls, acc.psi);
   // ---- h*torque on the parent, (hip, ankle): -ad*(w_p - w_c) - s*axis_p + k*(axis_p x axis_c)
   const V3 wA = lo3(r.L.w);
   const V3x2 t = fma3(-C.h_ad, pk3(r.T.w - wA, wA - hi3(r.L.w)),

@@ -90,22 +90,33 @@ struct ObsCols {
 // The part of the observation every env shares: [pos0, rot0, joint angles, vel0, ang0, joint vels,
 // clip(contact.vel), clip(contact.ang)] staged into this env's shared-memory row. The row was zeroed at kernel
 // start and its torso / Aux contact slots already hold the accumulated impulses (ContactAcc): clip in place.
-template <int KIND>
+template <int KIND, bool HAVE_PSI>   // HAVE_PSI: acc.psi holds the joint angles (step kernel: the last substep's)
 __device__ __forceinline__ void stage_common_obs(float* row, const Rig& r, const LegK& k, const ContactAcc& acc, int leg,
                                                  const DevConst& C) {
   using O = ObsCols<KIND>;
   // Revolute.angle_vel of the hip and the ankle, the two joints packed like in the substep:
   // hip psi = atan2(c0_A.c1_T, c0_A.c0_T), ankle psi = atan2(c2_B.(axA x c2_A), c2_A.c2_B); vel = (w_p - w_c).axis_p
-  const Cols cT = rot_cols(r.T);
-  Body2 L;
-  L.qw = pk(r.A.qw, r.B.qw); L.qx = pk(r.A.qx, r.B.qx); L.qy = pk(r.A.qy, r.B.qy); L.qz = pk(r.A.qz, r.B.qz);
-  const Cols2 cL = rot_cols2(L);
-  const V3 cA0 = lo3(cL.c0), cA1 = lo3(cL.c1), cA2 = lo3(cL.c2), cB2 = hi3(cL.c2);
-  const V3 axA = k.axc * cA0 + k.axs * cA1;
-  const V3 nA = k.axs * cA0 - k.axc * cA1;
-  const F2 psi = atan2_fast2(pk(dot(cA0, cT.c1), dot(cB2, nA)), pk(dot(cA0, cT.c0), dot(cA2, cB2)));
-  const float jah = lo(psi), jaa = hi(psi);
-  const float jvh = dot(r.T.w - r.A.w, cT.c2), jva = dot(r.A.w - r.B.w, axA);
+  float jah, jaa, jvh, jva;
+  if (HAVE_PSI) {
+    // only the two parent-side axes are needed: c2_T and axA = axc c0_A + axs c1_A
+    const float ts = r.T.qw, tx = r.T.qx, ty = r.T.qy, tz = r.T.qz, tz2 = tz + tz, ts2 = ts + ts;
+    const V3 c2T = mk(tz2 * tx + ts2 * ty, tz2 * ty - ts2 * tx, tz2 * tz + (ts * ts - (tx * tx + ty * ty + tz * tz)));
+    const Cols cA = rot_cols(r.A);
+    const V3 axA = k.axc * cA.c0 + k.axs * cA.c1;
+    jah = lo(acc.psi); jaa = hi(acc.psi);
+    jvh = dot(r.T.w - r.A.w, c2T); jva = dot(r.A.w - r.B.w, axA);
+  } else {
+    const Cols cT = rot_cols(r.T);
+    Body2 L;
+    L.qw = pk(r.A.qw, r.B.qw); L.qx = pk(r.A.qx, r.B.qx); L.qy = pk(r.A.qy, r.B.qy); L.qz = pk(r.A.qz, r.B.qz);
+    const Cols2 cL = rot_cols2(L);
+    const V3 cA0 = lo3(cL.c0), cA1 = lo3(cL.c1), cA2 = lo3(cL.c2), cB2 = hi3(cL.c2);
+    const V3 axA = k.axc * cA0 + k.axs * cA1;
+    const V3 nA = k.axs * cA0 - k.axc * cA1;
+    const F2 psi = atan2_fast2(pk(dot(cA0, cT.c1), dot(cB2, nA)), pk(dot(cA0, cT.c0), dot(cA2, cB2)));
+    jah = lo(psi); jaa = hi(psi);
+    jvh = dot(r.T.w - r.A.w, cT.c2); jva = dot(r.A.w - r.B.w, axA);
+  }
   row[O::ja + 2 * leg] = jah; row[O::ja + 2 * leg + 1] = jaa;
   row[O::jv + 2 * leg] = jvh; row[O::jv + 2 * leg + 1] = jva;
   float* cv = acc.cv;
@@ -358,7 +369,7 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
     }
   }
   __syncwarp();
-  stage_common_obs<KIND>(row, r, k, acc, leg, C);
+  stage_common_obs<KIND, true>(row, r, k, acc, leg, C);
   if (C.auto_reset == POBRAX_AUTORESET_CACHED && done_prev != 0.0f) steps = 0.0f;  // AutoResetWrapper.step head
   const int extra = ObsCols<KIND>::cv + 6 * C.nb;
 
@@ -712,7 +723,7 @@ reset_kernel(const __grid_constant__ DevConst C, const PobraxState S, const uint
     contacts2<KIND != POBRAX_ANT>(tmp, C, dA, dB, mT, mA, mB, leg, ct);
   }
   __syncwarp();
-  stage_common_obs<KIND>(row, r, k, ct, leg, C);
+  stage_common_obs<KIND, false>(row, r, k, ct, leg, C);
   const int extra = ObsCols<KIND>::cv + 6 * C.nb;
   if (KIND == POBRAX_ANT_TAG) {
     const bool vis = norm2_rn(__fsub_rn(aux2, r.T.p.x), __fsub_rn(aux3, r.T.p.y)) <= C.visible_radius;

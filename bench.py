@@ -28,10 +28,10 @@ FLOPS_PER_ENV_STEP = {'ant': 4.30e4, 'ant_heavenhell': 4.30e4, 'ant_tag': 4.30e4
 BYTES_PER_ENV_STEP = {'ant': 1332, 'ant_heavenhell': 1444, 'ant_tag': 1428, 'ant_gather': 2212}
 METRIC = 'env-steps/sec'
 # dram__bytes_read.sum + dram__bytes_write.sum of one step_kernel launch, from the committed ncu --set full captures
-# of the stationary regime (profiles/ncu_step_{hh,ant,ant_tag,ant_gather}_r2.txt; HeavenHell: 596.4 MB read + 982.4 MB
+# of the stationary regime (profiles/ncu_step_{hh,ant,ant_tag,ant_gather}_r2.txt; HeavenHell: 596.7 MB read + 982.7 MB
 # write at 1 Mi envs = 1506 B per env-step against 1444 algorithmic: no re-reads)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {('ant_heavenhell', 1 << 20): 1.5788e9, ('ant', 1 << 20): 1.4898e9,
-                                ('ant_tag', 1 << 20): 1.5819e9, ('ant_gather', 1 << 20): 2.229e9}
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {('ant_heavenhell', 1 << 20): 1.5793e9, ('ant', 1 << 20): 1.4909e9,
+                                ('ant_tag', 1 << 20): 1.5779e9, ('ant_gather', 1 << 20): 2.2180e9}
 
 
 def parse():

@@ -227,8 +227,20 @@ __device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, const fl
     const int n4 = (rows * D) >> 2;
     const float4* s4 = reinterpret_cast<const float4*>(stage);
     float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll 4
-    for (int i = lane; i < n4; i += 32) d4[i] = s4[i];   // unrolled: 4 LDS.128 in flight before the first STG.128
+    // warp-uniform trip counts (no per-lane predicates): blocks of 4 x 32 float4 with 4 LDS.128 in flight before the
+    // first STG.128, then single rounds, then the partial round
+    const int full = n4 >> 5;
+    const float4* sp = s4 + lane;
+    float4* dp = d4 + lane;
+    int j = 0;
+#pragma unroll 1
+    for (; j + 4 <= full; j += 4, sp += 128, dp += 128) {
+      const float4 a = sp[0], b = sp[32], c = sp[64], d = sp[96];
+      dp[0] = a; dp[32] = b; dp[64] = c; dp[96] = d;
+    }
+#pragma unroll 1
+    for (; j < full; ++j, sp += 32, dp += 32) dp[0] = sp[0];
+    if (lane < (n4 & 31)) dp[0] = sp[0];
 #pragma unroll 1
     for (int i = 4 * n4 + lane; i < rows * D; i += 32) dst[i] = stage[i];
   }
@@ -525,8 +537,10 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
   }
   if (valid) store_rig(reinterpret_cast<float4*>(S.qp), n, e, leg, r);
   const unsigned first_mask = __ballot_sync(kFull, reset_now && leg == 0);
-  unsigned fm8 = 0;
-  for (int i = 0; i < 8; ++i) fm8 |= ((first_mask >> (4 * i)) & 1u) << i;
+  unsigned fm8 = first_mask & 0x11111111u;   // bit 4 es -> bit es (every quad's lane 0)
+  fm8 = (fm8 | (fm8 >> 3)) & 0x03030303u;
+  fm8 = (fm8 | (fm8 >> 6)) & 0x000f000fu;
+  fm8 = (fm8 | (fm8 >> 12)) & 0xffu;
   __syncwarp();
   write_obs_rows<KIND == POBRAX_ANT_GATHER>(S.obs, S.first_obs, stage, D, C.obs_lo, C.obs_out, env0, C.n_envs, fm8, 0u, lane);
 }

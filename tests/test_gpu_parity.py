@@ -656,6 +656,26 @@ def test_fused_observability_mask(mask):
         assert torch.equal(a.buf['qp'], b.buf['qp']) and torch.equal(a.reward, b.reward) and torch.equal(a.done, b.done)
 
 
+def test_gather_column_range_and_cached_rows_through_the_out_of_line_obs_path():
+    """Gather's step kernel sends the uncommon observation-row work (a column subset, rows rewritten from the cached first
+    observation on autoreset) through the out-of-line write_obs_rows_general: same bits as the full-row kernel."""
+    n, lo, hi = 77, 29, 150
+    keys = P.keys_for(n, seed=13)
+    full = _make('ant_gather', n, episode_length=3, auto_reset=True)
+    part = _make('ant_gather', n, episode_length=3, auto_reset=True, obs_mask=(lo, hi))
+    assert part.observation_size == hi - lo
+    a, b = full.reset(keys), part.reset(keys)
+    assert torch.equal(a.obs[:, lo:hi], b.obs)
+    g = torch.Generator(device='cuda').manual_seed(6)
+    for t in range(8):   # episode_length 3: every env restarts from its cached first state at t = 2 and t = 5
+        act = torch.rand((n, 8), device='cuda', generator=g) * 2 - 1
+        a, b = full.step(a, act), part.step(b, act)
+        assert torch.equal(a.obs[:, lo:hi], b.obs), t
+        assert torch.equal(a.buf['qp'], b.buf['qp']) and torch.equal(a.reward, b.reward) and torch.equal(a.done, b.done)
+        if t in (2, 5):
+            assert bool(a.done.all()) and torch.equal(a.obs, a.info['first_obs'])
+
+
 def test_ragged_and_tiny_batches():
     """Batch sizes that do not fill a warp / CTA, and batch_size None (one env)."""
     for kind in KINDS:

@@ -479,7 +479,12 @@ __device__ __forceinline__ void contacts2(Rig2& r, const DevConst& C, V3 dA, V3 
   V3 gv, gw;
   foot_ground(B, C.s_foot * dB, C.r_leg, C.inv_m_leg, C, gv, gw);
   const bool hitT = C.r_torso - r.T.p.z > 0.0f;
+#ifdef POBRAX_TUNE_NO_RARE   // timing experiment only (WRONG physics): what the substep costs without the rare region,
+  if (hitT || (WALLS && (mT | mA | mB) != 0u)) acc.Bw.z += 1e-30f;   // table lookups kept alive
+  if (false) {
+#else
   if (__builtin_expect(hitT || (WALLS && (mT | mA | mB) != 0u), 0)) {  // the one divergent region of the substep (rare)
+#endif
     const V3 zero = mk(0.f, 0.f, 0.f);
     if (hitT || mT != 0u) {
       Imp t;

@@ -191,10 +191,7 @@ __device__ __forceinline__ void gather_readings(float* readings, const Body& T, 
 }
 
 // Shared epilogue pieces ------------------------------------------------------------------------------
-// Coalesced write of the warp's 8 staged observation rows (contiguous in obs[N][D]; 8*D floats start at a
-// 16-byte boundary because env0 is a multiple of 8). Rows in `first_mask` are then overwritten from the cached
-// first_obs (rare), rows in `skip_mask` are left untouched (reset_where_done).
-// The uncommon parts, out of line (one copy per library, keeps the step kernels' instruction footprint down): `copy` = the
+// The uncommon parts of write_obs_rows (below), out of line (one copy per library, keeps the step kernels' instruction footprint down): `copy` = the
 // column-subset / skip-mask row copy, then the rewrite of the rows in `first_mask` from the cached first_obs.
 __device__ __noinline__ void write_obs_rows_general(float* __restrict__ dst, const float* __restrict__ first,
                                                     const float* stage, int D, int lo, int Do, int rows, unsigned first_mask,
@@ -214,6 +211,9 @@ __device__ __noinline__ void write_obs_rows_general(float* __restrict__ dst, con
   }
 }
 
+// Coalesced write of the warp's 8 staged observation rows (contiguous in obs[N][D]; 8*D floats start at a
+// 16-byte boundary because env0 is a multiple of 8). Rows in `first_mask` are then overwritten from the cached
+// first_obs (rare), rows in `skip_mask` are left untouched (reset_where_done).
 template <bool OUTLINE>   // OUTLINE: the uncommon parts through write_obs_rows_general (Gather's step kernel)
 __device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, const float* __restrict__ first_obs,
                                                const float* stage, int D, int lo, int Do, long long env0, int n_envs,

@@ -27,13 +27,13 @@ namespace pobrax {
 #endif
 constexpr int kThreads = 128;             // reset kernels
 constexpr int kEnvsPerBlock = kThreads / 4;
-// Step kernels use small CTAs (1-2 warps): warps never wait for each other, so finer CTAs let the hardware
+// Step kernels use one-warp CTAs: warps never wait for each other, so finer CTAs let the hardware
 // scheduler balance warps of different cost (wall contacts) and shorten the tail. Measured per env family.
 template <int KIND> struct StepCfg {
 #ifdef POBRAX_TUNE_THREADS   // tuning builds: one CTA size for every family
   static constexpr int threads = POBRAX_TUNE_THREADS;
 #else
-  static constexpr int threads = KIND == POBRAX_ANT_GATHER ? 64 : 32;   // re-swept after the steady-state wall-path change
+  static constexpr int threads = 32;   // re-swept on the final kernels (Gather ran 2-warp CTAs while its epilogue was inlined: -1.5 % now)
 #endif
   static constexpr int envs = threads / 4;
   static constexpr int min_blocks = (KIND == POBRAX_ANT ? POBRAX_ANT_WARPS_PER_SMSP : POBRAX_WALL_WARPS_PER_SMSP) * (128 / threads);  // 96 / 128 registers

@@ -27,6 +27,21 @@ __global__ void k(float* out, int iters, float a0, float b0) {
   unsigned q[ILP], qa = threadIdx.x * 2654435761u;
 #pragma unroll
   for (int j = 0; j < ILP; ++j) { x[j] = pack(t + j, t - j); s[j] = t + j; m[j] = t * j; q[j] = threadIdx.x + j; bb[j] = pack(b0 + j * t, b0 - j * t); }
+  if (MODE == 15) {   // odd warps run only FFMA2, even warps only FFMA: the sub-partition's issue stream mixes, no warp's does
+    if ((threadIdx.x >> 7) & 1) {   // warps w and w + 4 share a sub-partition (warp id % 4): one of each kind per pair
+      for (int i = 0; i < iters; ++i)
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int j = 0; j < ILP; ++j) x[j] = ffma2(x[j], a, b);
+    } else {
+      for (int i = 0; i < 2 * iters; ++i)   // twice the instructions: both halves take about the same time
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int j = 0; j < ILP; ++j) s[j] = ffma(s[j], sa, sb);
+    }
+  } else
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -47,6 +62,7 @@ __global__ void k(float* out, int iters, float a0, float b0) {
         if (MODE == 12) { if (j < ILP / 2) x[j] = ffma2(x[j], a, b); else s[j] = ffma(s[j], sa, sb); }   // blocks of ILP/2
         if (MODE == 13) { x[j] = fmul2(x[j], a); q[j] = lop(q[j], qa); }
         if (MODE == 14) { s[j] = ffma(s[j], sa, sb); q[j] = lop(q[j], qa); }
+        if (MODE == 16) { if (u & 4) x[j] = ffma2(x[j], a, b); else s[j] = ffma(s[j], sa, sb); }   // blocks of 4 x ILP
       }
     }
   }
@@ -93,6 +109,8 @@ int main() {
     run<12, 8>("4 FFMA2 then 4 FFMA", out, w, 8 * (4 * 2 + 4), 8 * 8);
     run<13, 8>("FMUL2 + 2 ALU", out, w, 8 * 8, 8 * 24);
     run<14, 8>("FFMA + 2 ALU", out, w, 8 * 8, 8 * 24);
+    run<15, 8>("odd warps FFMA2, even warps 2x FFMA", out, w, 8 * 8 * 2, 8 * 8 * 1.5);
+    run<16, 8>("32 FFMA2 then 32 FFMA per warp", out, w, 8 * 8 * 1.5, 8 * 8);
   }
   return 0;
 }

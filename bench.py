@@ -369,7 +369,8 @@ def main_graft(args):
     clocks = sampler.stop(t0, t1) if sampler else None
     value = total * K / (ms * 1e-3)
     per_gpu = n * K / (ms * 1e-3)
-    launches = K * world
+    # kernels of this library inside the timed region: one step_kernel per step and rank (+ tag_rng_kernel for Tag)
+    launches = K * world * (2 if args.env == 'ant_tag' else 1)
 
     ms_early, _, _ = measure(n, early=True)
     early = {'value': total * K / (ms_early * 1e-3), 'ms_per_step': ms_early / K,

@@ -140,7 +140,9 @@ int pobrax_destroy(void* handle);
 
 /* keys: device uint32[N][2]. Writes every buffer of st (first_* if present). */
 int pobrax_reset(void* handle, const uint32_t* keys, PobraxState* st, void* stream);
-/* action: device float[N][8]. In-place update of st. */
+/* action: device float[N][8]. In-place update of st. One launch (the fused step kernel); for Ant-Tag batches above the
+ * small-batch threshold two: tag_rng_kernel draws the opponent's move of ant_tag.py:131-132 for the whole batch into
+ * an N-byte scratch buffer the handle owns (allocated in pobrax_create) and advances st->rng, then the step kernel. */
 int pobrax_step(void* handle, PobraxState* st, const float* action, void* stream);
 /* gym autoreset: where st->done != 0, replace qp/aux/obs by reset(keys[i]) and zero steps. */
 int pobrax_reset_where_done(void* handle, const uint32_t* keys, PobraxState* st, void* stream);

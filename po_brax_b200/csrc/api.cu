@@ -34,6 +34,7 @@ struct Handle {
   cudaTextureObject_t tip_tex = 0;
   float4* walls = nullptr;
   float2* grid = nullptr;
+  uint8_t* tag_choice = nullptr;         // Tag: the step's opponent moves (dev_const.h)
 };
 }  // namespace pobrax
 
@@ -507,6 +508,13 @@ extern "C" int pobrax_create(const PobraxParams* p, int device, void** handle) {
     C.tip_tex = (unsigned long long)h->tip_tex;
   }
   C.walls = h->walls;
+  C.tag_choice = nullptr;
+  if (C.env_kind == POBRAX_ANT_TAG) {
+    if ((e = cudaMalloc(&h->tag_choice, (size_t)C.n_envs)) != cudaSuccess) {
+      cudaSetDevice(prev); pobrax_destroy(h); return fail_cuda("cudaMalloc(tag move scratch)", e);
+    }
+    C.tag_choice = h->tag_choice;
+  }
   {  // per-device kernel attributes + occupancy for THIS handle's device (a process may hold handles on several GPUs)
     const char* what = "";
     if ((e = pobrax::setup_device(C, (size_t)prop.sharedMemPerBlockOptin, &what)) != cudaSuccess) {
@@ -532,6 +540,7 @@ extern "C" int pobrax_destroy(void* handle) {
   if (h->tip_array) cudaFreeArray(h->tip_array);
   if (h->walls) cudaFree(h->walls);
   if (h->grid) cudaFree(h->grid);
+  if (h->tag_choice) cudaFree(h->tag_choice);
   cudaSetDevice(prev);
   delete h;
   return 0;

@@ -37,6 +37,10 @@ struct DevConst {
   int32_t episode_length, auto_reset, substeps, track_metrics, n_walls, has_rng;
   int32_t prefetch_ctas;                     // step kernel: L2 prefetch distance in CTAs (0: this CTA's own, harmless)
   int32_t small_batch_envs;                  // batches up to this size run step_kernel_small (kernels.cu StepCfg)
+  // Tag, batches above small_batch_envs: the opponent's move (ant_tag.py:131-132: split + randint) is drawn for the
+  // whole batch by tag_rng_kernel, one THREAD per env (5 threefry blocks per env), ahead of the step kernel, which
+  // reads it here -- inside the step kernel the 4 lanes of an env cost 12 block executions per env.
+  uint8_t* tag_choice;                       // handle-owned device scratch [n_envs], null for the other env families
   float h, dt, gravity_z, vel_damp, ang_damp, baumgarte, friction, elasticity;
   float m_torso, m_leg, inv_m_torso, inv_m_leg, r_torso, r_leg;
   float k_joint, sd_joint, ad_joint, ls_joint, act_strength;

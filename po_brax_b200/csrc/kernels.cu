@@ -332,9 +332,13 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
 
   // Tag: the opponent's move choice depends only on info['rng'] (ant_tag.py:131-132), not on the physics:
   // drawn here, while the state loads are still in flight, instead of serialised behind the substep loop.
+  // Large batches (the throughput instantiation) get it from tag_rng_kernel, which has also advanced info['rng'].
+  constexpr bool TAG_PRE = KIND == POBRAX_ANT_TAG && !SMALL;
   int tag_choice = 0;
   Key tag_knext; tag_knext.k0 = tag_knext.k1 = 0u;
-  if (KIND == POBRAX_ANT_TAG) {
+  if (TAG_PRE) {
+    tag_choice = (int)C.tag_choice[e];
+  } else if (KIND == POBRAX_ANT_TAG) {
     Key key; key.k0 = S.rng[2 * e]; key.k1 = S.rng[2 * e + 1];
     Key k1;   // the 4 lanes of an env hold the same key: each pair of lanes shares the two blocks of a split
     split2_pair(key, lane, tag_knext, k1);
@@ -444,7 +448,7 @@ step_kernel(const __grid_constant__ DevConst C, const PobraxState S, const float
       row[extra] = vis ? nx : 0.0f;
       row[extra + 1] = vis ? ny : 0.0f;
       if (valid) {
-        S.rng[2 * e] = knext.k0; S.rng[2 * e + 1] = knext.k1;
+        if (!TAG_PRE) { S.rng[2 * e] = knext.k0; S.rng[2 * e + 1] = knext.k1; }
         S.aux[2 * n + e] = nx; S.aux[3 * n + e] = ny; S.aux[4 * n + e] = 1.0f;
       }
     }
@@ -950,13 +954,29 @@ cudaError_t setup_device(DevConst& C, size_t smem_limit, const char** what) {
   return cudaErrorInvalidValue;
 }
 
+// AntTagEnv._step_target's random draw for the whole batch (ant_tag.py:131-132): rng, rng1 = split(rng);
+// choice = randint(rng1, (), 0, 4). One thread per env, info['rng'] advanced in place, the choice left in the handle's
+// scratch for the step kernel launched behind it on the same stream. Same bits as the in-kernel form (threefry.cuh).
+__global__ void __launch_bounds__(256) tag_rng_kernel(uint32_t* __restrict__ rng, uint8_t* __restrict__ choice, int n) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const uint2 k = reinterpret_cast<const uint2*>(rng)[e];
+  Key key; key.k0 = k.x; key.k1 = k.y;
+  Key knext, k1;
+  split2(key, knext, k1);
+  choice[e] = (uint8_t)randint4(k1);
+  reinterpret_cast<uint2*>(rng)[e] = make_uint2(knext.k0, knext.k1);
+}
+
 template <int KIND>
 static cudaError_t launch_step_t(const DevConst& C, const PobraxState& S, const float* action, cudaStream_t st) {
   const int blocks = (C.n_envs + StepCfg<KIND>::envs - 1) / StepCfg<KIND>::envs;
-  if (C.n_envs <= C.small_batch_envs)
+  if (C.n_envs <= C.small_batch_envs) {
     step_kernel<KIND, true><<<blocks, StepCfg<KIND>::threads, step_smem_bytes<KIND>(C), st>>>(C, S, action);
-  else
+  } else {
+    if (KIND == POBRAX_ANT_TAG) tag_rng_kernel<<<(C.n_envs + 255) / 256, 256, 0, st>>>(S.rng, C.tag_choice, C.n_envs);
     step_kernel<KIND, false><<<blocks, StepCfg<KIND>::threads, step_smem_bytes<KIND>(C), st>>>(C, S, action);
+  }
   return cudaGetLastError();
 }
 

@@ -588,16 +588,16 @@ __device__ __forceinline__ void default_leg(Rig& r, const LegK& k, float qh, flo
   r.B.w = qrot(mk(k.axc * va, k.axs * va, 0.f), qA);
 }
 
+// The reset of ONE group of 8 consecutive envs by one warp (group = env0 / 8).
 template <int KIND>
-__global__ void __launch_bounds__(kThreads, 2)
-reset_kernel(const __grid_constant__ DevConst C, const PobraxState S, const uint32_t* __restrict__ keys,
-             const float2* __restrict__ grid_xy, int only_done, uint32_t* __restrict__ chain) {
-  extern __shared__ float smem[];
+__device__ __forceinline__ void reset_group(const DevConst& C, const PobraxState& S, const uint32_t* __restrict__ keys,
+                                            const float2* __restrict__ grid_xy, int only_done, uint32_t* __restrict__ chain,
+                                            float* smem, long long group) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int leg = lane & 3, es = lane >> 2;
   const int D = C.obs_dim;
   const size_t n = (size_t)C.n_envs;
-  const long long env0 = ((long long)blockIdx.x * kEnvsPerBlock) + warp * 8;
+  const long long env0 = group * 8;
   const long long env_raw = env0 + es;
   const bool valid = env_raw < (long long)n;
   const size_t e = valid ? (size_t)env_raw : n - 1;
@@ -792,6 +792,41 @@ reset_kernel(const __grid_constant__ DevConst C, const PobraxState S, const uint
   __syncwarp();
   write_obs_rows<false>(S.obs, S.obs, stage, D, C.obs_lo, C.obs_out, env0, C.n_envs, 0u, sk8, lane);
   if (!only_done && S.first_obs) write_obs_rows<false>(S.first_obs, S.obs, stage, D, C.obs_lo, C.obs_out, env0, C.n_envs, 0u, sk8, lane);
+}
+
+// only_done = 0: warp w of the grid resets group w. only_done = 1 (gym autoreset, wrappers.py:245-262): warp w SCANS the
+// done flags of groups 32 w .. 32 w + 31 (one group per lane) and resets the few that hold a finished env -- with one CTA
+// per 32 envs the launch spent 0.11 ms at 1 Mi envs dispatching 32 768 CTAs that had nothing to do.
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 2)
+reset_kernel(const __grid_constant__ DevConst C, const PobraxState S, const uint32_t* __restrict__ keys,
+             const float2* __restrict__ grid_xy, int only_done, uint32_t* __restrict__ chain) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const long long n_groups = ((long long)C.n_envs + 7) / 8;
+  unsigned todo = (w < n_groups) ? 1u : 0u;   // only_done = 0: this warp's own group
+  long long base = w;
+  if (only_done) {
+    const long long g = w * 32 + lane;
+    bool any = false;
+    if (g < n_groups) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long e = g * 8 + i;
+        if (e < (long long)C.n_envs) any |= S.done[e] != 0.0f;
+      }
+    }
+    todo = __ballot_sync(kFull, any);
+    base = w * 32;
+  }
+#pragma unroll 1
+  while (todo) {   // one code copy of the group reset for both modes
+    const int j = __ffs(todo) - 1;
+    todo &= todo - 1;
+    reset_group<KIND>(C, S, keys, grid_xy, only_done, chain, smem, base + j);
+    __syncwarp();   // the staging rows are reused by the next group
+  }
 }
 
 // --------------------------------------------------------------------------- brax.QP <-> packed state
@@ -992,7 +1027,8 @@ __global__ void chain_advance_kernel(uint32_t* chain, int n_envs) {
 template <int KIND>
 static cudaError_t launch_reset_t(const DevConst& C, const PobraxState& S, const uint32_t* keys, const float2* grid,
                                   int only_done, uint32_t* chain, cudaStream_t st) {
-  const int blocks = (C.n_envs + kEnvsPerBlock - 1) / kEnvsPerBlock;
+  const long long groups = ((long long)C.n_envs + 7) / 8, per_cta = (kThreads / 32) * (only_done ? 32 : 1);
+  const int blocks = (int)((groups + per_cta - 1) / per_cta);
   reset_kernel<KIND><<<blocks, kThreads, reset_smem_bytes<KIND>(C), st>>>(C, S, keys, grid, only_done, chain);
   if (chain) chain_advance_kernel<<<1, 1, 0, st>>>(chain, C.n_envs);
   return cudaGetLastError();

@@ -12,9 +12,9 @@ for sync_free, graph, copy in ((False, False, True), (True, False, True), (True,
     e = envs.create_gym_env('ant_heavenhell', batch_size=n, seed=0, cuda_graph=graph, copy=copy)
     e.sync_free = sync_free
     e.reset()
-    a = torch.rand((n, 8), device='cuda') * 2 - 1
-    for _ in range(10): e.step(a)
+    a = torch.rand((64, n, 8), device='cuda', generator=torch.Generator(device='cuda').manual_seed(1)) * 2 - 1
+    for i in range(50): e.step(a[i % 64])          # i.i.d. actions like bench.py (a constant action is a gait)
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    for _ in range(50): e.step(a)
-    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 50
+    for i in range(100): e.step(a[(50 + i) % 64])
+    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 100
     print('gym step, sync_free', sync_free, 'cuda_graph', graph, 'copy', copy, 'ms/step', round(dt * 1e3, 3), 'env-steps/s', f'{n / dt:.3e}')

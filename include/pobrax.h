@@ -158,6 +158,13 @@ int pobrax_unpack_qp(void* handle, const float* qp, const float* aux, float* pos
 int pobrax_pack_qp(void* handle, const float* pos, const float* rot, const float* vel, const float* ang,
                    float* qp, float* aux, void* stream);
 
+/* EvalGymWrapper.step (envs/wrappers.py:202-219) in one launch, all pointers device memory of n elements (sums: 4
+ * doubles = finished episodes, sum of their returns, discounted returns and lengths -- what get_stats() averages):
+ * returns += r; lengths += 1; disc_returns += r * cur_discount; cur_discount *= discount; where done: the episode goes
+ * into sums and its four slots restart (0, 0, 0, 1). */
+int pobrax_eval_update(const float* reward, const float* done, float* returns, float* disc_returns, long long* lengths,
+                       float* cur_discount, double* sums, float discount, int n, void* stream);
+
 /* jax.random.split(key, n): key = host uint32[2]; out = device uint32[n][2] (rows first..first+count). */
 int pobrax_split_keys(const uint32_t key[2], int n, int first, int count, uint32_t* out, void* stream);
 

@@ -66,6 +66,7 @@ EXPORTS = {
     'pobrax_unpack_qp': (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),
     'pobrax_pack_qp': (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_void_p]),
     'pobrax_split_pairs': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'pobrax_eval_update': (C.c_int, [C.c_void_p] * 7 + [C.c_float, C.c_int, C.c_void_p]),
     'pobrax_fp32_probe': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]),
     'pobrax_split_keys': (C.c_int, [C.POINTER(C.c_uint32), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }

@@ -22,6 +22,8 @@ cudaError_t launch_pack(const DevConst& C, const float* pos, const float* rot, c
                         float* qp, float* aux, cudaStream_t st);
 cudaError_t launch_split_keys(const uint32_t key[2], int n, int first, int count, uint32_t* out, cudaStream_t st);
 cudaError_t launch_fma_probe(float* out, int blocks, int iters, cudaStream_t st);
+cudaError_t launch_eval_update(const float* reward, const float* done, float* ret, float* dret, long long* len, float* disc,
+                               double* sums, float discount, int n, cudaStream_t st);
 cudaError_t launch_split_pairs(const uint32_t* keys, int n, uint32_t* a, uint32_t* b, cudaStream_t st);
 cudaError_t setup_device(DevConst& C, size_t smem_limit, const char** what);
 
@@ -626,6 +628,17 @@ extern "C" int pobrax_split_keys(const uint32_t key[2], int n, int first, int co
   if (n <= 0 || first < 0 || count < 0 || first + count > n) return fail("pobrax_split_keys: bad range");
   cudaError_t e = pobrax::launch_split_keys(key, n, first, count, out, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? 0 : fail_cuda("pobrax_split_keys launch", e);
+}
+
+extern "C" int pobrax_eval_update(const float* reward, const float* done, float* returns, float* disc_returns,
+                                  long long* lengths, float* cur_discount, double* sums, float discount, int n,
+                                  void* stream) {
+  if (!reward || !done || !returns || !disc_returns || !lengths || !cur_discount || !sums)
+    return fail("pobrax_eval_update: null argument");
+  if (n <= 0) return fail("pobrax_eval_update: n must be positive");
+  cudaError_t e = pobrax::launch_eval_update(reward, done, returns, disc_returns, lengths, cur_discount, sums, discount, n,
+                                             static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? 0 : fail_cuda("pobrax_eval_update launch", e);
 }
 
 extern "C" int pobrax_fp32_probe(float* out, int blocks, int iters, void* stream, double* flops) {

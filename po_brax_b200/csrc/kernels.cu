@@ -1084,6 +1084,46 @@ cudaError_t launch_split_keys(const uint32_t key[2], int n, int first, int count
 
 }  // namespace pobrax
 
+namespace pobrax {
+// EvalGymWrapper.step (/root/reference/po_brax/envs/wrappers.py:202-219) as ONE launch: episode return, discounted
+// return, length and running discount per env; finished episodes go into four double sums (count, return, discounted
+// return, length -- what get_stats() averages) and their slots restart. The torch form was ~25 elementwise / reduction
+// launches per gym step: 3x the gym step itself at scratch.py's 16 envs.
+__global__ void __launch_bounds__(256) eval_update_kernel(const float* __restrict__ reward, const float* __restrict__ done,
+                                                          float* __restrict__ ret, float* __restrict__ dret,
+                                                          long long* __restrict__ len, float* __restrict__ disc,
+                                                          double* __restrict__ sums, float discount, int n) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  double c = 0.0, sr = 0.0, sd = 0.0, sl = 0.0;
+  if (e < n) {
+    const float r = reward[e], g = disc[e];
+    float R = __fadd_rn(ret[e], r), DR = __fadd_rn(dret[e], __fmul_rn(r, g)), G = __fmul_rn(g, discount);
+    long long L = len[e] + 1;
+    if (done[e] != 0.0f) {
+      c = 1.0; sr = (double)R; sd = (double)DR; sl = (double)L;
+      R = 0.0f; DR = 0.0f; L = 0; G = 1.0f;
+    }
+    ret[e] = R; dret[e] = DR; len[e] = L; disc[e] = G;
+  }
+  if (__any_sync(kFull, c != 0.0)) {   // finished episodes are rare: one set of atomics per warp that has any
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      c += __shfl_xor_sync(kFull, c, m); sr += __shfl_xor_sync(kFull, sr, m);
+      sd += __shfl_xor_sync(kFull, sd, m); sl += __shfl_xor_sync(kFull, sl, m);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(sums + 0, c); atomicAdd(sums + 1, sr); atomicAdd(sums + 2, sd); atomicAdd(sums + 3, sl);
+    }
+  }
+}
+
+cudaError_t launch_eval_update(const float* reward, const float* done, float* ret, float* dret, long long* len, float* disc,
+                               double* sums, float discount, int n, cudaStream_t st) {
+  eval_update_kernel<<<(n + 255) / 256, 256, 0, st>>>(reward, done, ret, dret, len, disc, sums, discount, n);
+  return cudaGetLastError();
+}
+}  // namespace pobrax
+
 // ------------------------------------------------------------------------- FP32 FMA peak probe (bench)
 // 8 independent FMA chains per thread; used by bench.py to measure the non-tensor FP32 roof on the box.
 namespace pobrax {

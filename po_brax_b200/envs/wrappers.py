@@ -15,7 +15,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from .. import random as prandom
+from .. import _lib, random as prandom
 from .env import Env
 
 Box = namedtuple('Box', ['low', 'high', 'shape', 'dtype'])
@@ -291,19 +291,19 @@ class EvalGymWrapper:
 
     def step(self, action):
         o, r, d, info = self.env.step(action)
-        self.episode_returns += r
-        self.episode_lengths += 1
-        self.discounted_episode_returns += r * self.current_discount
-        self.current_discount *= self._discount
-        dm = d != 0
-        dd = dm.to(torch.float64)
-        self._sums += torch.stack([dd.sum(), (self.episode_returns.double() * dd).sum(),
-                                   (self.discounted_episode_returns.double() * dd).sum(),
-                                   (self.episode_lengths.double() * dd).sum()])
-        self.episode_returns = torch.where(dm, torch.zeros_like(self.episode_returns), self.episode_returns)
-        self.discounted_episode_returns = torch.where(dm, torch.zeros_like(r), self.discounted_episode_returns)
-        self.episode_lengths = torch.where(dm, torch.zeros_like(self.episode_lengths), self.episode_lengths)
-        self.current_discount = torch.where(dm, torch.ones_like(r), self.current_discount)
+        # one launch (pobrax_eval_update) instead of ~25 elementwise / reduction launches: same update, same sums
+        rr = r.reshape(-1)
+        dd = d.reshape(-1)
+        if rr.dtype != torch.float32 or not rr.is_contiguous():
+            rr = rr.float().contiguous()
+        if dd.dtype != torch.float32 or not dd.is_contiguous():
+            dd = dd.float().contiguous()
+        with torch.cuda.device(rr.device):
+            _lib.check(_lib.load().pobrax_eval_update(
+                rr.data_ptr(), dd.data_ptr(), self.episode_returns.data_ptr(), self.discounted_episode_returns.data_ptr(),
+                self.episode_lengths.data_ptr(), self.current_discount.data_ptr(), self._sums.data_ptr(),
+                float(self._discount), int(self.num_envs), torch.cuda.current_stream(rr.device).cuda_stream),
+                'pobrax_eval_update')
         return o, r, d, info
 
     def get_stats(self):

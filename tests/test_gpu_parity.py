@@ -494,6 +494,33 @@ def test_gym_adapters_follow_the_reference_key_chain():
     assert fresh.obs.shape == (n, 114)
 
 
+@pytest.mark.parametrize('batch', [48, None])
+def test_eval_gym_wrapper_statistics_equal_the_reference_recount(batch):
+    """EvalGymWrapper (wrappers.py:175-229) through the fused pobrax_eval_update launch: the three means of get_stats()
+    equal a host recount that follows the reference line by line (running sums, queues of finished episodes, nanmean)."""
+    from po_brax_b200 import envs
+    disc = 0.9
+    e = envs.create_gym_env('ant_tag', batch_size=batch, seed=5, episode_length=6, eval_metrics=True, discount=disc)
+    e.reset()
+    n = batch or 1
+    ret, dret, ln, cur = np.zeros(n), np.zeros(n), np.zeros(n, int), np.ones(n)
+    rq, dq, lq = [], [], []
+    g = torch.Generator(device='cuda').manual_seed(9)
+    for t in range(20):
+        a = torch.rand((n, 8) if batch else (8,), device='cuda', generator=g) * 2 - 1
+        o, r, d, info = e.step(a)
+        r = np.atleast_1d(np.asarray(r.cpu(), np.float64)); d = np.atleast_1d(np.asarray(d.cpu())) != 0
+        ret += r; ln += 1; dret += r * cur; cur *= disc
+        for i in np.nonzero(d)[0]:
+            rq.append(ret[i]); dq.append(dret[i]); lq.append(ln[i])
+        ret[d] = 0; dret[d] = 0; ln[d] = 0; cur[d] = 1
+    st = e.get_stats()
+    assert len(rq) >= 3 * n
+    assert abs(st['charts/mean_episodic_return'] - np.mean(rq)) < 1e-5
+    assert abs(st['charts/mean_discounted_episodic_return'] - np.mean(dq)) < 1e-5
+    assert abs(st['charts/mean_episodic_length'] - np.mean(lq)) < 1e-9
+
+
 @pytest.mark.parametrize('kind', ['ant_tag', 'ant_gather'])
 def test_gym_autoreset_device_key_chain_equals_host_round_trip(kind):
     """AutoresetVmapGymWrapper.step (wrappers.py:245-262): with the gym key chain on the device

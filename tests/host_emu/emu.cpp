@@ -43,6 +43,7 @@ cudaError_t launch_pack(const DevConst&, const float*, const float*, const float
 cudaError_t launch_split_keys(const uint32_t*, int, int, int, uint32_t*, cudaStream_t) { return cudaErrorNotSupported; }
 cudaError_t launch_fma_probe(float*, int, int, cudaStream_t) { return cudaErrorNotSupported; }
 cudaError_t launch_split_pairs(const uint32_t*, int, uint32_t*, uint32_t*, cudaStream_t) { return cudaErrorNotSupported; }
+cudaError_t launch_eval_update(const float*, const float*, float*, float*, long long*, float*, double*, float, int, cudaStream_t) { return cudaErrorNotSupported; }
 cudaError_t setup_device(DevConst&, size_t, const char** what) { *what = "host emulator"; return cudaErrorNotSupported; }
 }  // namespace pobrax
 

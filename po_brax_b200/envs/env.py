@@ -17,6 +17,8 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)   # private but stable accessor (also what triton uses)
+
 from .. import _lib
 
 KINDS = {'ant': _lib.ANT, 'ant_heavenhell': _lib.ANT_HEAVENHELL, 'ant_gather': _lib.ANT_GATHER,
@@ -258,6 +260,7 @@ class Env:
             raise RuntimeError('po_brax_b200 envs live on a CUDA device')
         if self.device.index is None:
             self.device = torch.device('cuda', torch.cuda.current_device())
+        self._dev_index = int(self.device.index)
         # create(batch_size=None) adds no VmapWrapper (__init__.py:64): State fields carry no batch axis. The kernels
         # always run a batch; an unbatched env is a batch of one whose State strips the axis.
         self.unbatched = not batch_size    # `if batch_size:` in the reference: None and 0 both mean un-vmapped
@@ -385,6 +388,10 @@ class Env:
         return self
 
     def _stream(self):
+        # the raw cudaStream_t of torch's current stream on this env's device; torch.cuda.current_stream() builds a
+        # Stream object per call (6 us: a third of a small-batch step's host time), the C accessor does not
+        if _raw_stream is not None:
+            return C.c_void_p(_raw_stream(self._dev_index))
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _alloc(self) -> Dict[str, Optional[torch.Tensor]]:
